@@ -1,0 +1,150 @@
+"""Pins the CPU oracle (oracle/) to the reference: its golden files, outputs of the reference
+itself (tests/golden/make_golden.py) and Random123 known-answer vectors.  CPU only."""
+import gzip
+import io
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import ALL_TAGS, load_golden, oracle_params
+from oracle import (closed_form_site_probability, mil_inference, mod_ratio, noisy_or_site_probability,
+                    philox4x32_10, read_probabilities, sample_indices, sample_indices_mt19937)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+        ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+        ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+         [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+    ]
+    for ctr, key, want in kat:
+        got = philox4x32_10(np.array(ctr, np.uint32), np.array(key, np.uint32))
+        assert [int(v) for v in got] == want
+
+
+def test_sample_indices_range_and_determinism():
+    a = sample_indices(5, 2**33 + 3, 37, 64, 20)
+    b = sample_indices(5, 2**33 + 3, 37, 64, 20)
+    c = sample_indices(5, 2**33 + 4, 37, 64, 20)
+    assert a.shape == (64, 20) and a.min() >= 0 and a.max() < 37
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    # iteration i does not depend on n_iters (counter-based)
+    assert np.array_equal(sample_indices(5, 9, 37, 8, 20), sample_indices(5, 9, 37, 64, 20)[:8])
+    # n_samples not a multiple of 4 is a prefix of the 4-word calls
+    assert np.array_equal(sample_indices(5, 9, 37, 8, 7), sample_indices(5, 9, 37, 8, 8)[:, :7])
+
+
+def test_sample_indices_uniform():
+    idx = sample_indices(0, 11, 50, 20000, 20).ravel()
+    counts = np.bincount(idx, minlength=50)
+    expected = len(idx) / 50
+    chi2 = ((counts - expected) ** 2 / expected).sum()
+    assert chi2 < 100.0  # 49 dof; P(chi2 > 100) ~ 2e-5
+
+
+def test_mt19937_replay_matches_numpy_choice():
+    p = np.linspace(0, 1, 41, dtype=np.float32)
+    np.random.seed(3)
+    drawn = np.random.choice(p, 5 * 20, replace=True).reshape(5, 20)
+    idx = sample_indices_mt19937(3, 41, 5, 20)
+    assert np.array_equal(drawn, p[idx])
+
+
+@pytest.mark.parametrize("tag", ALL_TAGS)
+def test_read_probabilities_match_reference_model(tag, synthetic_inputs):
+    g = load_golden(tag)
+    params = oracle_params(tag)
+    n_reads = np.diff(synthetic_inputs["read_off"])
+    kmer_rows = np.repeat(synthetic_inputs["kmer_idx"], n_reads, axis=0)
+    p = read_probabilities(params, synthetic_inputs["feats"], kmer_rows)
+    # reference = torch CPU forward (fixtures); the restatement differs only by summation order
+    assert np.max(np.abs(p - g["read_prob"])) <= 2e-6
+    np.testing.assert_allclose(p, g["read_prob"], rtol=2e-4, atol=1e-30)
+
+
+@pytest.mark.parametrize("tag", ALL_TAGS)
+def test_mil_inference_matches_literal_forward(tag, synthetic_inputs):
+    """Factored oracle (p once per read, table look-ups) == the reference's literal MIL forward
+    on the gathered bags, on the shared Philox index stream."""
+    g = load_golden(tag)
+    params = oracle_params(tag)
+    rp, sp, mc = mil_inference(params, synthetic_inputs["feats"], synthetic_inputs["read_off"], synthetic_inputs["kmer_idx"],
+                               n_iters=int(g["n_iters"]), seed=int(g["seed"]), site_id_base=int(g["site_id_base"]),
+                               n_samples=int(g["n_samples"]), read_threshold=float(g["threshold"]))
+    assert np.max(np.abs(sp - g["site_prob"])) <= 1e-5
+    assert np.array_equal(mc, g["mod_count"])
+    assert np.allclose(mc / np.diff(synthetic_inputs["read_off"]), g["mod_ratio"], rtol=0, atol=0)
+
+
+def test_bundled_read_probs_match_reference_goldens(bundled_flat, golden_dir):
+    """Reference golden data.indiv_proba.csv.gz with the reference test's own tolerance
+    (m6anet/tests/test_inference.py:32: np.allclose default rtol 1e-5, atol 1e-8)."""
+    params = oracle_params("HCT116_RNA002")
+    b = bundled_flat
+    n_reads = np.diff(b["read_off"])
+    kmer_rows = np.repeat(b["kmer_idx"], n_reads, axis=0)
+    p = read_probabilities(params, b["feats"], kmer_rows)
+    assert np.max(np.abs(p - b["read_prob"])) <= 1e-6
+    gold = pd.read_csv(os.path.join(golden_dir, "bundled", "data.indiv_proba.csv.gz"))
+    mine = pd.DataFrame({"transcript_id": np.repeat(b["tx_id"], n_reads), "transcript_position": np.repeat(b["tx_pos"], n_reads),
+                         "read_index": b["read_id"].astype(np.int64), "probability_modified": p.astype(np.float64)})
+    keys = ["transcript_id", "transcript_position", "read_index"]
+    gold = gold.sort_values(keys).reset_index(drop=True)
+    mine = mine.sort_values(keys).reset_index(drop=True)
+    assert np.all(gold["transcript_id"] == mine["transcript_id"])
+    assert np.all(gold["transcript_position"] == mine["transcript_position"])
+    assert np.all(gold["read_index"] == mine["read_index"])
+    assert np.allclose(gold["probability_modified"], mine["probability_modified"])
+
+
+def test_bundled_site_outputs_match_reference_goldens(bundled_flat, golden_dir):
+    """Reference golden data.site_proba.csv.gz: mod_ratio allclose, site probability atol 1e-2
+    (m6anet/tests/test_inference.py:36-37; the reference tests at 10000 iterations)."""
+    params = oracle_params("HCT116_RNA002")
+    b = bundled_flat
+    rp, sp, mc = mil_inference(params, b["feats"], b["read_off"], b["kmer_idx"], n_iters=10000, seed=0,
+                               read_threshold=0.033379376)
+    gold = pd.read_csv(os.path.join(golden_dir, "bundled", "data.site_proba.csv.gz"))
+    mine = pd.DataFrame({"transcript_id": b["tx_id"], "transcript_position": b["tx_pos"],
+                         "probability_modified": sp.astype(np.float64), "mod_ratio": mc / np.diff(b["read_off"])})
+    keys = ["transcript_id", "transcript_position"]
+    gold = gold.sort_values(keys).reset_index(drop=True)
+    mine = mine.sort_values(keys).reset_index(drop=True)
+    assert len(gold) == len(mine) == 101
+    assert np.all(gold["transcript_id"] == mine["transcript_id"])
+    assert np.allclose(gold["mod_ratio"], mine["mod_ratio"])
+    assert np.allclose(gold["probability_modified"], mine["probability_modified"], atol=1e-2)
+    # RNG sanity against the closed form E = 1-(1-mean p)^20
+    for s in range(len(sp)):
+        e = closed_form_site_probability(rp[b["read_off"][s]:b["read_off"][s + 1]])
+        assert abs(sp[s] - e) < 3 * 0.5 / np.sqrt(10000) + 1e-6
+
+
+def test_mt19937_replay_matches_reference_function(bundled_flat):
+    """oracle noisy-OR on the replayed MT19937 indices == the reference's `_calculate_site_proba`
+    itself (fixture computed by the reference right after np.random.seed(0))."""
+    b = bundled_flat
+    for s, want in zip(b["replay_sites"], b["replay_site_prob"]):
+        p = b["read_prob"][b["read_off"][s]:b["read_off"][s + 1]]
+        idx = sample_indices_mt19937(int(b["replay_seed"]), len(p), int(b["replay_n_iters"]), 20)
+        got = noisy_or_site_probability(p, idx)
+        assert got.dtype == np.float32
+        assert got == want  # same library calls, bit-identical
+
+
+def test_mod_ratio_threshold_is_float32():
+    thr = 0.033379376
+    p = np.array([np.float32(thr), np.nextafter(np.float32(thr), np.float32(0))], dtype=np.float32)
+    assert mod_ratio(p, thr) == 0.5
+
+
+def test_empty_site_and_single_read():
+    params = oracle_params("HCT116_RNA002")
+    feats = np.zeros((1, 9), np.float32)
+    rp, sp, mc = mil_inference(params, feats, np.array([0, 0, 1]), np.array([[0, 1, 2], [3, 4, 5]]), n_iters=4)
+    assert np.isnan(sp[0]) and mc[0] == 0
+    assert np.isclose(sp[1], 1 - (1 - rp[0]) ** 20, atol=1e-6)
