@@ -1,0 +1,131 @@
+/*
+ * m6anet_b200 -- C ABI of the B200-native m6anet MIL-inference hot path.
+ *
+ * One call scores a batch of DRACH sites: read encoder (k-mer embedding + 2-layer MLP + sigmoid
+ * read classifier) over every read, mod_ratio, and the Monte-Carlo noisy-OR site probability
+ * averaged over n_iters samplings of n_samples reads.
+ *
+ * The reference is pure Python and has no FFI; each entry point below names the reference
+ * interface it replaces (paths relative to the reference's m6anet/ package):
+ *
+ *   m6a_model_create        MILModel(toml).load_state_dict(...)            scripts/inference.py:88-90,
+ *                            (weights of the Sequential read encoder)        model/model.py:40-69
+ *   m6a_mil_infer_f32       the body of run_inference per batch:            utils/inference_utils.py:35-54
+ *                              get_read_representation + probability_layer  (:35-37)
+ *                              group_results                                (:48-51,107-140)
+ *                              mod_ratio                                    (:53)
+ *                              calculate_site_proba/_calculate_site_proba   (:54,74-104)
+ *   m6a_mil_infer_host_f32  the same, including features.to(device) / probs.cpu()  (:35-36,41)
+ *   m6a_philox_indices      np.random.choice index draw                     (:85)
+ *
+ * Conventions: plain C types only; no exceptions cross the boundary; every function returns an
+ * int status (0 = ok, <0 = M6A_E*, >0 = a cudaError_t value) readable with m6a_strerror().
+ * Device entry points enqueue on `stream` of the CURRENT device and return without
+ * synchronising; the caller owns every buffer.
+ */
+#ifndef M6ANET_B200_H_
+#define M6ANET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M6A_VERSION 100 /* 0.1.0 */
+
+#define M6A_OK 0
+#define M6A_EINVAL (-1)       /* NULL pointer / negative size / inconsistent argument        */
+#define M6A_EUNSUPPORTED (-2) /* model dimensions outside the compiled kernel limits         */
+#define M6A_EALIGN (-3)       /* a device buffer is not aligned as documented                */
+#define M6A_ERANGE (-4)       /* a site has more reads than the mode allows                  */
+#define M6A_ENOMEM (-5)       /* host allocation failed                                      */
+
+/* Compiled limits of the kernel (see m6anet_b200/csrc/m6a_layout.h). */
+#define M6A_N_SIG 9          /* signal features per read: 3 positions x (dwell, sd, mean)   */
+#define M6A_H2 32            /* width of the second Linear block                            */
+#define M6A_H1_MAX 152       /* max width of the first Linear block (shipped models: 150)   */
+#define M6A_MAX_READS_EXPLICIT 65535 /* uint16 explicit indices                             */
+
+/*
+ * Read-encoder parameters, HOST pointers, row-major float32, eval-mode BatchNorm already folded
+ * into w1/b1 by the caller (m6anet_b200/model.py does this in float64).
+ * Layout mirrors the reference state_dict:
+ *   emb [n_kmer, emb_dim]          read_level_encoder.1.embedding_layer.weight   (NULL when emb_dim == 0)
+ *   w1  [h1, n_sig + 3*emb_dim]    read_level_encoder.3.layers.0.weight (x BN scale); signal columns first
+ *   b1  [h1]
+ *   w2  [h2, h1], b2 [h2]          read_level_encoder.4.layers.0.{weight,bias}
+ *   w3  [h2], b3 [1]               pooling_filter.probability_layer.0.{weight,bias}
+ */
+typedef struct {
+  const float *emb;
+  const float *w1, *b1;
+  const float *w2, *b2;
+  const float *w3, *b3;
+  int32_t n_kmer, emb_dim, n_sig, h1, h2;
+} m6a_weights_t;
+
+typedef struct m6a_model m6a_model_t; /* opaque: packed weight image resident on one device */
+
+int m6a_version(void);
+const char *m6a_strerror(int status);
+
+/* Packs the weights into the kernel's shared-memory image and uploads it to the current CUDA
+ * device (synchronous).  The model may be used from any stream of that device. */
+int m6a_model_create(const m6a_weights_t *w, m6a_model_t **out);
+int m6a_model_destroy(m6a_model_t *model);
+
+/*
+ * Score n_sites sites.  All data pointers are DEVICE pointers.
+ *
+ *   feats       [total_reads, 9] float32, normalised, site-contiguous rows (4-byte aligned; a
+ *               16-byte aligned base enables the TMA bulk-copy path, otherwise plain loads are used)
+ *   read_off    [n_sites + 1] int64 CSR offsets into feats rows; read_off[0] may be > 0
+ *               (a shard of a larger buffer); non-decreasing
+ *   kmer_idx    [n_sites, 3] int32 five-mer ids of the site's 7-mer (ignored when emb_dim == 0; may be NULL then)
+ *   site_id_base  global id of site 0: the RNG counter is (site_id_base + s), so results do not
+ *               depend on how sites are sharded over GPUs
+ *   n_samples   reads per bag (the reference hard-codes 20), 1..64
+ *   n_iters     Monte-Carlo iterations (>= 1)
+ *   seed        Philox key
+ *   sample_idx  optional [n_sites, n_iters, n_samples] uint16 explicit indices (parity / replay
+ *               mode, requires every site to have <= 65535 reads); NULL => on-device Philox4x32-10
+ *               with index = (word * n_reads) >> 32
+ *   read_threshold  float32 threshold of mod_ratio (p >= threshold)
+ * outputs
+ *   read_prob   [total_reads] float32, indexed like feats rows (absolute row index)
+ *   site_prob   [n_sites] float32; NaN for a site without reads
+ *   mod_count   [n_sites] int32 number of reads with p >= read_threshold
+ *               (mod_ratio = mod_count / n_reads, formed by the host in float64 like np.mean)
+ */
+int m6a_mil_infer_f32(const m6a_model_t *model, const float *feats, const int64_t *read_off,
+                      const int32_t *kmer_idx, int64_t n_sites, int64_t total_reads,
+                      int64_t site_id_base, int32_t n_samples, int32_t n_iters, uint64_t seed,
+                      const uint16_t *sample_idx, float read_threshold, float *read_prob,
+                      float *site_prob, int32_t *mod_count, void *stream);
+
+/*
+ * Same computation with HOST buffers (read_off[0] must be 0 here).  Sites are cut into
+ * `n_chunks` read-balanced chunks (0 => automatic) that are copied, scored and copied back on
+ * rotating CUDA streams so that H2D, kernel and D2H overlap.  Synchronous.  Pinned host buffers
+ * overlap best; pageable ones still work.  sample_idx is not supported on this path.
+ */
+int m6a_mil_infer_host_f32(const m6a_model_t *model, const float *feats, const int64_t *read_off,
+                           const int32_t *kmer_idx, int64_t n_sites, int64_t site_id_base,
+                           int32_t n_samples, int32_t n_iters, uint64_t seed, float read_threshold,
+                           float *read_prob, float *site_prob, int32_t *mod_count, int32_t n_chunks);
+
+/* Writes the device index stream of one site: out [n_iters, n_samples] int32 (DEVICE pointer).
+ * Test hook proving the device generator equals oracle/philox.py bit for bit. */
+int m6a_philox_indices(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters,
+                       int32_t n_samples, int32_t *out, void *stream);
+
+/* Launch geometry of the last m6a_mil_infer_f32 call on this thread (for bench/roofline
+ * reporting): grid, block, dynamic smem bytes, sites per tile, number of kernel launches. */
+int m6a_last_launch(int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *sites_per_tile,
+                    int32_t *n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M6ANET_B200_H_ */

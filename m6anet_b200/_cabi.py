@@ -1,0 +1,84 @@
+"""ctypes binding of the C ABI declared in include/m6anet_b200.h.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``make -C m6anet_b200/csrc``.
+There is deliberately no fallback: if the library is missing, using the symbols raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libm6anet_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+EXPORTS = (
+    "m6a_version", "m6a_strerror", "m6a_model_create", "m6a_model_destroy", "m6a_mil_infer_f32",
+    "m6a_mil_infer_host_f32", "m6a_philox_indices", "m6a_last_launch",
+)
+
+
+class M6AWeights(C.Structure):
+    """struct m6a_weights_t"""
+    _fields_ = [
+        ("emb", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("w3", C.c_void_p), ("b3", C.c_void_p),
+        ("n_kmer", C.c_int32), ("emb_dim", C.c_int32), ("n_sig", C.c_int32), ("h1", C.c_int32), ("h2", C.c_int32),
+    ]
+
+
+class M6AError(RuntimeError):
+    def __init__(self, status: int, where: str):
+        self.status = status
+        msg = lib().m6a_strerror(status).decode() if _lib is not None else "?"
+        super().__init__(f"{where}: m6anet_b200 status {status} ({msg})")
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libm6anet_b200.so for sm_100a with nvcc (in-tree)."""
+    res = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("building libm6anet_b200.so failed:\n" + res.stderr[-4000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension was not built. Run `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` or `make -C m6anet_b200/csrc`. m6anet_b200 has no CPU fallback for the hot path.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+    L.m6a_version.restype = C.c_int
+    L.m6a_version.argtypes = []
+    L.m6a_strerror.restype = C.c_char_p
+    L.m6a_strerror.argtypes = [C.c_int]
+    L.m6a_model_create.restype = C.c_int
+    L.m6a_model_create.argtypes = [C.POINTER(M6AWeights), C.POINTER(vp)]
+    L.m6a_model_destroy.restype = C.c_int
+    L.m6a_model_destroy.argtypes = [vp]
+    L.m6a_mil_infer_f32.restype = C.c_int
+    L.m6a_mil_infer_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, u64, vp, f32, vp, vp, vp, vp]
+    L.m6a_mil_infer_host_f32.restype = C.c_int
+    L.m6a_mil_infer_host_f32.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, u64, f32, vp, vp, vp, i32]
+    L.m6a_philox_indices.restype = C.c_int
+    L.m6a_philox_indices.argtypes = [u64, i64, i32, i32, i32, vp, vp]
+    L.m6a_last_launch.restype = C.c_int
+    L.m6a_last_launch.argtypes = [C.POINTER(i32)] * 5
+    _lib = L
+    return L
+
+
+def check(status: int, where: str) -> None:
+    if status != 0:
+        raise M6AError(status, where)

@@ -1,0 +1,302 @@
+// C ABI of the m6anet MIL-inference hot path (declared in include/m6anet_b200.h).
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/m6anet_b200.h"
+#include "m6a_kernel.h"
+
+using namespace m6a;
+
+struct m6a_model {
+  DeviceModel dev;
+  void* d_image;
+  void* d_ctab;
+  int device;
+  int n_sms;
+};
+
+static thread_local LaunchInfo g_last = {0, 0, 0, 0};
+static thread_local int g_last_launches = 0;
+
+extern "C" int m6a_version(void) { return M6A_VERSION; }
+
+extern "C" const char* m6a_strerror(int status) {
+  switch (status) {
+    case M6A_OK: return "ok";
+    case M6A_EINVAL: return "invalid argument";
+    case M6A_EUNSUPPORTED: return "model dimensions not supported by the compiled kernel";
+    case M6A_EALIGN: return "buffer alignment";
+    case M6A_ERANGE: return "value out of range for this mode";
+    case M6A_ENOMEM: return "host allocation failed";
+    default: break;
+  }
+  if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+  return "unknown m6anet_b200 status";
+}
+
+#define M6A_CUDA(expr)                                  \
+  do {                                                  \
+    cudaError_t _e = (expr);                            \
+    if (_e != cudaSuccess) return static_cast<int>(_e); \
+  } while (0)
+
+extern "C" int m6a_model_create(const m6a_weights_t* w, m6a_model_t** out) {
+  if (w == nullptr || out == nullptr) return M6A_EINVAL;
+  *out = nullptr;
+  if (!w->w1 || !w->b1 || !w->w2 || !w->b2 || !w->w3 || !w->b3) return M6A_EINVAL;
+  if (w->n_sig != kNSig || w->h2 != kH2 || w->h1 < 1 || w->h1 > kH1Max) return M6A_EUNSUPPORTED;
+  if (w->emb_dim < 0 || w->emb_dim > 64) return M6A_EUNSUPPORTED;
+  if (w->emb_dim > 0 && (w->emb == nullptr || w->n_kmer < 1 || w->n_kmer > 4096)) return M6A_EINVAL;
+
+  const int h1 = w->h1, E = w->emb_dim, in1 = kNSig + kKmerPos * E;
+  const int n_kmer = E > 0 ? w->n_kmer : 1;
+
+  WeightImage* img = static_cast<WeightImage*>(calloc(1, sizeof(WeightImage)));
+  if (!img) return M6A_ENOMEM;
+  for (int j = 0; j < h1; ++j) {
+    for (int k = 0; k < kNSig; ++k) img->l12[j][k] = w->w1[static_cast<size_t>(j) * in1 + k];
+    for (int k = 0; k < kH2; ++k) img->l12[j][kW2Off + k] = w->w2[static_cast<size_t>(k) * h1 + j];
+  }
+  for (int k = 0; k < kH2; ++k) {
+    img->b2[k] = w->b2[k];
+    img->w3[k] = w->w3[k];
+  }
+  img->b3 = w->b3[0];
+  img->h1 = h1;
+
+  // ctab[t][kmer][j]: per k-mer-position contribution of the embedding to Linear-1 (table 0 carries b1)
+  std::vector<float> ctab(static_cast<size_t>(kKmerPos) * n_kmer * kH1Max, 0.0f);
+  for (int t = 0; t < kKmerPos; ++t)
+    for (int k = 0; k < n_kmer; ++k)
+      for (int j = 0; j < h1; ++j) {
+        float c = (t == 0) ? w->b1[j] : 0.0f;
+        for (int d = 0; d < E; ++d)
+          c = fmaf(w->w1[static_cast<size_t>(j) * in1 + kNSig + t * E + d], w->emb[static_cast<size_t>(k) * E + d], c);
+        ctab[(static_cast<size_t>(t) * n_kmer + k) * kH1Max + j] = c;
+      }
+
+  m6a_model* m = new (std::nothrow) m6a_model();
+  if (!m) {
+    free(img);
+    return M6A_ENOMEM;
+  }
+  cudaError_t e = cudaGetDevice(&m->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->n_sms, cudaDevAttrMultiProcessorCount, m->device);
+  m->d_image = nullptr;
+  m->d_ctab = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_image, sizeof(WeightImage));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_ctab, ctab.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_image, img, sizeof(WeightImage), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_ctab, ctab.data(), ctab.size() * sizeof(float), cudaMemcpyHostToDevice);
+  free(img);
+  if (e != cudaSuccess) {
+    if (m->d_image) cudaFree(m->d_image);
+    if (m->d_ctab) cudaFree(m->d_ctab);
+    delete m;
+    return static_cast<int>(e);
+  }
+  m->dev.image = static_cast<const WeightImage*>(m->d_image);
+  m->dev.ctab = static_cast<const float*>(m->d_ctab);
+  m->dev.n_kmer = n_kmer;
+  m->dev.h1 = h1;
+  m->dev.emb_dim = E;
+  *out = m;
+  return M6A_OK;
+}
+
+extern "C" int m6a_model_destroy(m6a_model_t* model) {
+  if (!model) return M6A_OK;
+  cudaFree(model->d_image);
+  cudaFree(model->d_ctab);
+  delete model;
+  return M6A_OK;
+}
+
+static int sites_per_tile_for(long long n_sites, long long total_reads) {
+  const long long avg = std::max<long long>(1, (total_reads + n_sites - 1) / std::max<long long>(1, n_sites));
+  long long g = kChunkReads / avg;
+  return static_cast<int>(std::min<long long>(kSitesPerTileMax, std::max<long long>(1, g)));
+}
+
+extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, const int64_t* read_off,
+                                 const int32_t* kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
+                                 int32_t n_samples, int32_t n_iters, uint64_t seed, const uint16_t* sample_idx,
+                                 float read_threshold, float* read_prob, float* site_prob, int32_t* mod_count,
+                                 void* stream) {
+  if (!model || n_sites < 0 || total_reads < 0) return M6A_EINVAL;
+  if (n_samples < 1 || n_samples > 64 || n_iters < 1) return M6A_EINVAL;
+  if (n_sites == 0) return M6A_OK;
+  if (!read_off || !site_prob || !mod_count) return M6A_EINVAL;
+  if (total_reads > 0 && (!feats || !read_prob)) return M6A_EINVAL;
+  if (model->dev.emb_dim > 0 && !kmer_idx) return M6A_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(feats) & 3u) || (reinterpret_cast<uintptr_t>(read_off) & 7u)) return M6A_EALIGN;
+
+  KernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.model = model->dev;
+  a.feats = feats;
+  a.read_off = read_off;
+  a.kmer_idx = kmer_idx;
+  a.sample_idx = sample_idx;
+  a.read_prob = read_prob;
+  a.site_prob = site_prob;
+  a.mod_count = mod_count;
+  a.n_sites = n_sites;
+  a.sites_per_tile = sites_per_tile_for(n_sites, total_reads);
+  a.n_tiles = (n_sites + a.sites_per_tile - 1) / a.sites_per_tile;
+  a.site_id_base = site_id_base;
+  a.feats_bytes = static_cast<unsigned long long>(total_reads) * (kNSig * sizeof(float));
+  a.seed = seed;
+  a.n_samples = n_samples;
+  a.n_iters = n_iters;
+  a.iters_per_lane = (n_iters + 32 * kSlabCap - 1) / (32 * kSlabCap);
+  a.n_slabs = (n_iters + 32 * a.iters_per_lane - 1) / (32 * a.iters_per_lane);
+  a.read_threshold = read_threshold;
+  a.feats_tma_ok = (reinterpret_cast<uintptr_t>(feats) & 15u) == 0;
+
+  LaunchInfo info;
+  cudaError_t e = launch_mil_infer(a, model->n_sms, static_cast<cudaStream_t>(stream), &info);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  g_last = info;
+  g_last_launches = 1;
+  return M6A_OK;
+}
+
+extern "C" int m6a_philox_indices(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters, int32_t n_samples,
+                                  int32_t* out, void* stream) {
+  if (!out || n_reads < 1 || n_iters < 1 || n_samples < 1) return M6A_EINVAL;
+  cudaError_t e = launch_philox_indices(seed, static_cast<uint64_t>(site_id), static_cast<uint32_t>(n_reads), n_iters,
+                                        n_samples, out, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? M6A_OK : static_cast<int>(e);
+}
+
+extern "C" int m6a_last_launch(int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* sites_per_tile,
+                               int32_t* n_launches) {
+  if (grid) *grid = g_last.grid;
+  if (block) *block = g_last.block;
+  if (smem_bytes) *smem_bytes = g_last.smem_bytes;
+  if (sites_per_tile) *sites_per_tile = g_last.sites_per_tile;
+  if (n_launches) *n_launches = g_last_launches;
+  return M6A_OK;
+}
+
+// ---- host-buffer path: chunked, stream-pipelined H2D -> kernel -> D2H --------------------------------
+namespace {
+struct Slot {
+  cudaStream_t stream = nullptr;
+  float* d_feats = nullptr;
+  int64_t* d_off = nullptr;
+  int32_t* d_kmer = nullptr;
+  float* d_rp = nullptr;
+  float* d_sp = nullptr;
+  int32_t* d_mc = nullptr;
+  int64_t* h_off = nullptr;  // pinned staging for re-based offsets
+};
+}  // namespace
+
+extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model, const float* feats, const int64_t* read_off,
+                                      const int32_t* kmer_idx, int64_t n_sites, int64_t site_id_base,
+                                      int32_t n_samples, int32_t n_iters, uint64_t seed, float read_threshold,
+                                      float* read_prob, float* site_prob, int32_t* mod_count, int32_t n_chunks) {
+  if (!model || n_sites < 0) return M6A_EINVAL;
+  if (n_sites == 0) return M6A_OK;
+  if (!read_off || !site_prob || !mod_count) return M6A_EINVAL;
+  if (read_off[0] != 0) return M6A_EINVAL;
+  const int64_t total_reads = read_off[n_sites];
+  if (total_reads < 0) return M6A_EINVAL;
+  if (total_reads > 0 && (!feats || !read_prob)) return M6A_EINVAL;
+  if (model->dev.emb_dim > 0 && !kmer_idx) return M6A_EINVAL;
+
+  // chunk boundaries: balanced by reads, cut at site boundaries
+  if (n_chunks <= 0) {
+    const int64_t bytes = total_reads * kNSig * 4;
+    n_chunks = static_cast<int>(std::min<int64_t>(64, std::max<int64_t>(1, bytes / (64ll << 20))));
+    if (n_chunks > 1 && n_chunks < 4) n_chunks = 4;
+  }
+  if (n_chunks > n_sites) n_chunks = static_cast<int>(n_sites);
+  std::vector<int64_t> cut(n_chunks + 1, 0);
+  cut[n_chunks] = n_sites;
+  for (int c = 1; c < n_chunks; ++c) {
+    const int64_t target = total_reads * c / n_chunks;
+    const int64_t* p = std::lower_bound(read_off + cut[c - 1], read_off + n_sites, target);
+    cut[c] = std::max<int64_t>(cut[c - 1], std::min<int64_t>(p - read_off, n_sites));
+  }
+  int64_t max_sites = 0, max_reads = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    max_sites = std::max(max_sites, cut[c + 1] - cut[c]);
+    max_reads = std::max(max_reads, read_off[cut[c + 1]] - read_off[cut[c]]);
+  }
+
+  const int n_slots = std::min(3, n_chunks);
+  Slot slots[3];
+  int rc = M6A_OK;
+  auto cleanup = [&]() {
+    for (int s = 0; s < n_slots; ++s) {
+      Slot& sl = slots[s];
+      if (sl.stream) cudaStreamSynchronize(sl.stream);
+      cudaFree(sl.d_feats); cudaFree(sl.d_off); cudaFree(sl.d_kmer);
+      cudaFree(sl.d_rp); cudaFree(sl.d_sp); cudaFree(sl.d_mc);
+      if (sl.h_off) cudaFreeHost(sl.h_off);
+      if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+  };
+#define M6A_TRY(expr)                       \
+  do {                                      \
+    cudaError_t _e = (expr);                \
+    if (_e != cudaSuccess) {                \
+      rc = static_cast<int>(_e);            \
+      cleanup();                            \
+      return rc;                            \
+    }                                       \
+  } while (0)
+
+  for (int s = 0; s < n_slots; ++s) {
+    Slot& sl = slots[s];
+    M6A_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    M6A_TRY(cudaMalloc(&sl.d_feats, std::max<int64_t>(1, max_reads) * kNSig * sizeof(float)));
+    M6A_TRY(cudaMalloc(&sl.d_off, (max_sites + 1) * sizeof(int64_t)));
+    M6A_TRY(cudaMalloc(&sl.d_kmer, max_sites * kKmerPos * sizeof(int32_t)));
+    M6A_TRY(cudaMalloc(&sl.d_rp, std::max<int64_t>(1, max_reads) * sizeof(float)));
+    M6A_TRY(cudaMalloc(&sl.d_sp, max_sites * sizeof(float)));
+    M6A_TRY(cudaMalloc(&sl.d_mc, max_sites * sizeof(int32_t)));
+    M6A_TRY(cudaMallocHost(&sl.h_off, (max_sites + 1) * sizeof(int64_t)));
+  }
+
+  int launches = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    Slot& sl = slots[c % n_slots];
+    const int64_t sa = cut[c], sb = cut[c + 1], ns = sb - sa;
+    if (ns == 0) continue;
+    const int64_t ra = read_off[sa], nr = read_off[sb] - ra;
+    M6A_TRY(cudaStreamSynchronize(sl.stream));  // slot (and its pinned offset staging) free again
+    for (int64_t i = 0; i <= ns; ++i) sl.h_off[i] = read_off[sa + i] - ra;
+    M6A_TRY(cudaMemcpyAsync(sl.d_off, sl.h_off, (ns + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sl.stream));
+    if (nr > 0)
+      M6A_TRY(cudaMemcpyAsync(sl.d_feats, feats + ra * kNSig, nr * kNSig * sizeof(float), cudaMemcpyHostToDevice,
+                              sl.stream));
+    if (kmer_idx)
+      M6A_TRY(cudaMemcpyAsync(sl.d_kmer, kmer_idx + sa * kKmerPos, ns * kKmerPos * sizeof(int32_t),
+                              cudaMemcpyHostToDevice, sl.stream));
+    rc = m6a_mil_infer_f32(model, sl.d_feats, sl.d_off, kmer_idx ? sl.d_kmer : nullptr, ns, nr, site_id_base + sa,
+                           n_samples, n_iters, seed, nullptr, read_threshold, sl.d_rp, sl.d_sp, sl.d_mc, sl.stream);
+    if (rc != M6A_OK) {
+      cleanup();
+      return rc;
+    }
+    ++launches;
+    if (nr > 0)
+      M6A_TRY(cudaMemcpyAsync(read_prob + ra, sl.d_rp, nr * sizeof(float), cudaMemcpyDeviceToHost, sl.stream));
+    M6A_TRY(cudaMemcpyAsync(site_prob + sa, sl.d_sp, ns * sizeof(float), cudaMemcpyDeviceToHost, sl.stream));
+    M6A_TRY(cudaMemcpyAsync(mod_count + sa, sl.d_mc, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+  }
+  for (int s = 0; s < n_slots; ++s) M6A_TRY(cudaStreamSynchronize(slots[s].stream));
+  cleanup();
+  g_last_launches = launches;
+  return M6A_OK;
+#undef M6A_TRY
+}

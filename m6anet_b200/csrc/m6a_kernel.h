@@ -1,0 +1,52 @@
+// Internal interface between the C-ABI layer (m6a_api.cu) and the kernels (m6a_kernel.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "m6a_layout.h"
+
+namespace m6a {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kReadsPerThread = 2;
+constexpr int kChunkReads = kThreads * kReadsPerThread;  // feature rows staged per bulk copy
+constexpr int kSitesPerTileMax = 32;
+constexpr int kQCap = 4096;             // q = 1-p entries kept in shared memory per tile
+constexpr int kSlabCap = 64;            // Monte-Carlo partial sums per site
+constexpr int kCStride = kH1Max + 1;    // odd stride: per-lane site rows hit distinct banks
+
+struct KernelArgs {
+  DeviceModel model;
+  const float* feats;
+  const int64_t* read_off;
+  const int32_t* kmer_idx;
+  const uint16_t* sample_idx;
+  float* read_prob;
+  float* site_prob;
+  int32_t* mod_count;
+  long long n_sites;
+  long long n_tiles;
+  long long site_id_base;
+  unsigned long long feats_bytes;
+  unsigned long long seed;
+  int sites_per_tile;
+  int n_samples;
+  int n_iters;
+  int n_slabs;         // ceil(n_iters / (32 * iters_per_lane)) <= kSlabCap
+  int iters_per_lane;  // ceil(n_iters / (32 * kSlabCap))
+  float read_threshold;
+  bool feats_tma_ok;   // feats base 16-byte aligned -> cp.async.bulk staging
+};
+
+struct LaunchInfo {
+  int grid, block, smem_bytes, sites_per_tile;
+};
+
+size_t smem_bytes();
+cudaError_t launch_mil_infer(const KernelArgs& a, int n_sms, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_philox_indices(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
+                                  int32_t* out, cudaStream_t stream);
+
+}  // namespace m6a

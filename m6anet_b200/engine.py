@@ -1,0 +1,127 @@
+"""MilEngine: Python handle on the C ABI (include/m6anet_b200.h).  PyTorch is used only for device
+memory and streams; every number comes out of the CUDA kernel."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _cabi
+from .weights import EncoderWeights
+
+DEFAULT_N_SAMPLES = 20   # the literal 20 of reference utils/inference_utils.py:54
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class MilEngine:
+    """One packed model resident on one CUDA device."""
+
+    def __init__(self, weights: EncoderWeights, device: "int | str | None" = None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("m6anet_b200 needs a CUDA device (the hot path has no CPU fallback)")
+        self._torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError(f"MilEngine needs a cuda device, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.weights = weights
+        self._lib = _cabi.lib()
+        keep = {k: np.ascontiguousarray(getattr(weights, k), dtype=np.float32)
+                for k in ("w1", "b1", "w2", "b2", "w3", "b3")}
+        emb = None if weights.emb is None else np.ascontiguousarray(weights.emb, dtype=np.float32)
+        w = _cabi.M6AWeights(emb=_ptr(emb), w1=_ptr(keep["w1"]), b1=_ptr(keep["b1"]), w2=_ptr(keep["w2"]),
+                             b2=_ptr(keep["b2"]), w3=_ptr(keep["w3"]), b3=_ptr(keep["b3"]),
+                             n_kmer=weights.n_kmer, emb_dim=weights.emb_dim, n_sig=weights.n_sig,
+                             h1=weights.h1, h2=weights.h2)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.m6a_model_create(C.byref(w), C.byref(handle)), "m6a_model_create")
+        self._handle = handle
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.m6a_model_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device-resident call (m6a_mil_infer_f32) -------------------------------------------------
+    def infer_device(self, feats, read_off, kmer_idx, n_iters: int, seed: int = 0, site_id_base: int = 0,
+                     n_samples: int = DEFAULT_N_SAMPLES, read_threshold: float = 0.033379376,
+                     sample_idx=None, out=None, stream=None):
+        """feats [R,9] f32, read_off [S+1] i64, kmer_idx [S,3] i32 -- CUDA tensors on self.device.
+        Enqueues on `stream` (default: torch's current stream); returns (read_prob, site_prob, mod_count)
+        CUDA tensors without synchronising."""
+        torch = self._torch
+        assert feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()
+        assert read_off.is_cuda and read_off.dtype == torch.int64 and read_off.is_contiguous()
+        n_sites = read_off.numel() - 1
+        total_reads = feats.shape[0]
+        if kmer_idx is not None:
+            assert kmer_idx.is_cuda and kmer_idx.dtype == torch.int32 and kmer_idx.is_contiguous()
+            assert kmer_idx.numel() == 3 * n_sites
+        if sample_idx is not None:
+            assert sample_idx.is_cuda and sample_idx.dtype == torch.uint16 and sample_idx.is_contiguous()
+            assert sample_idx.numel() == n_sites * n_iters * n_samples
+        if out is None:
+            read_prob = torch.empty(total_reads, dtype=torch.float32, device=self.device)
+            site_prob = torch.empty(n_sites, dtype=torch.float32, device=self.device)
+            mod_count = torch.empty(n_sites, dtype=torch.int32, device=self.device)
+        else:
+            read_prob, site_prob, mod_count = out
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device) if stream is None else stream
+            rc = self._lib.m6a_mil_infer_f32(
+                self._handle, feats.data_ptr(), read_off.data_ptr(), None if kmer_idx is None else kmer_idx.data_ptr(),
+                n_sites, total_reads, site_id_base, n_samples, n_iters, seed & 0xFFFFFFFFFFFFFFFF,
+                None if sample_idx is None else sample_idx.data_ptr(), read_threshold,
+                read_prob.data_ptr(), site_prob.data_ptr(), mod_count.data_ptr(), st.cuda_stream)
+        _cabi.check(rc, "m6a_mil_infer_f32")
+        return read_prob, site_prob, mod_count
+
+    # ---- host-buffer call (m6a_mil_infer_host_f32): chunked H2D / kernel / D2H pipeline -------------
+    def infer_host(self, feats: np.ndarray, read_off: np.ndarray, kmer_idx: Optional[np.ndarray], n_iters: int,
+                   seed: int = 0, site_id_base: int = 0, n_samples: int = DEFAULT_N_SAMPLES,
+                   read_threshold: float = 0.033379376, n_chunks: int = 0, out=None
+                   ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        n_sites = len(read_off) - 1
+        if kmer_idx is not None:
+            kmer_idx = np.ascontiguousarray(kmer_idx, dtype=np.int32)
+        if out is None:
+            read_prob = np.empty(feats.shape[0], dtype=np.float32)
+            site_prob = np.empty(n_sites, dtype=np.float32)
+            mod_count = np.empty(n_sites, dtype=np.int32)
+        else:
+            read_prob, site_prob, mod_count = out
+        with self._torch.cuda.device(self.device):
+            rc = self._lib.m6a_mil_infer_host_f32(
+                self._handle, _ptr(feats), _ptr(read_off), _ptr(kmer_idx), n_sites, site_id_base, n_samples, n_iters,
+                seed & 0xFFFFFFFFFFFFFFFF, read_threshold, _ptr(read_prob), _ptr(site_prob), _ptr(mod_count), n_chunks)
+        _cabi.check(rc, "m6a_mil_infer_host_f32")
+        return read_prob, site_prob, mod_count
+
+    def philox_indices(self, seed: int, site_id: int, n_reads: int, n_iters: int, n_samples: int = DEFAULT_N_SAMPLES):
+        torch = self._torch
+        out = torch.empty((n_iters, n_samples), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.m6a_philox_indices(seed & 0xFFFFFFFFFFFFFFFF, site_id, n_reads, n_iters, n_samples,
+                                              out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        _cabi.check(rc, "m6a_philox_indices")
+        return out
+
+    def last_launch(self) -> dict:
+        v = [C.c_int32() for _ in range(5)]
+        self._lib.m6a_last_launch(*[C.byref(x) for x in v])
+        return dict(zip(("grid", "block", "smem_bytes", "sites_per_tile", "n_launches"), (x.value for x in v)))

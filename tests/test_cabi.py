@@ -1,0 +1,81 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/m6anet_b200.h declares (no compute calls without a GPU)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "m6anet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(m6a_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from m6anet_b200 import _cabi
+    if not os.path.exists(_cabi.LIB_PATH):
+        _cabi.build()
+    return _cabi.lib()
+
+
+def test_header_symbols_are_exported(lib):
+    from m6anet_b200 import _cabi
+    syms = declared_symbols()
+    assert syms and set(syms) == set(_cabi.EXPORTS)
+    for s in syms:
+        assert getattr(lib, s) is not None
+
+
+def test_version_and_strerror(lib):
+    assert lib.m6a_version() == 100
+    assert lib.m6a_strerror(0) == b"ok"
+    assert b"invalid" in lib.m6a_strerror(-1)
+    assert b"supported" in lib.m6a_strerror(-2)
+
+
+def test_library_targets_sm100a():
+    import subprocess
+    from m6anet_b200 import _cabi
+    out = subprocess.run(["cuobjdump", "-lelf", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from m6anet_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _cabi.lib()
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from m6anet_b200 import weights as W
+    from m6anet_b200.engine import MilEngine
+    w = W.from_npz(os.path.join(ROOT, "m6anet_b200", "assets", "model_states", "rna002_hct116.npz"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        MilEngine(w)
+
+
+def test_batchnorm_fold_matches_unfolded_oracle():
+    """host logic: the float64 BatchNorm fold reproduces the unfolded restatement to float32 rounding."""
+    import numpy as np
+    from m6anet_b200 import weights as W
+    from oracle import ReadEncoderParams, read_probabilities
+    npz = os.path.join(ROOT, "m6anet_b200", "assets", "model_states", "rna004_hek293t_glori.npz")
+    w = W.from_npz(npz)
+    assert (w.h1, w.h2, w.n_sig, w.emb_dim, w.n_kmer) == (150, 32, 9, 2, 66)
+    raw = ReadEncoderParams.from_npz(npz)
+    folded = ReadEncoderParams(w.emb, w.w1, w.b1, np.ones(150, np.float32), np.zeros(150, np.float32),
+                               np.zeros(150, np.float32), np.ones(150, np.float32), w.w2, w.b2, w.w3.reshape(1, -1), w.b3,
+                               bn_eps=0.0)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((4096, 9), dtype=np.float32)
+    k = rng.integers(0, 66, size=(4096, 3))
+    assert np.max(np.abs(read_probabilities(raw, x, k) - read_probabilities(folded, x, k))) <= 2e-6
