@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- DRACH sites/sec of the MIL-inference hot path at num_iterations=1000.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): synthetic
+1M DRACH sites x 50 reads, HCT116_RNA002 weights, num_iterations=1000, 20 reads per bag.  For N > 1
+the SAME 1M-site job is sharded by contiguous site ranges (strong scaling), one NCCL all-gather of the
+per-site outputs at the end of every step.
+
+A "step" is one pass of the hot path over the whole job.  One JSON line is printed by rank 0:
+  value      sites/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        sites/s through the host-buffer C-ABI call (pinned host inputs, H2D + kernel + D2H
+             pipelined inside the timed region)
+  roofline   achieved algorithmic GB/s of the fused kernel vs the measured HBM peak
+  cpu_baseline  the oracle's CPU port of the reference path on a bounded sample (rank 0, N=1)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "DRACH sites/sec at num_iterations=1000"
+UNIT = "sites/s"
+MODELS = {
+    "HCT116_RNA002": ("rna002_hct116.npz", 0.033379376),
+    "arabidopsis_RNA002": ("rna002_arabidopsis_virc.npz", 0.0032978046219796),
+    "HEK293T_RNA004": ("rna004_hek293t_glori.npz", 0.033379376),
+}
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sites", type=int, default=1_000_000)
+    ap.add_argument("--reads", type=int, default=50)
+    ap.add_argument("--iters", type=int, default=1000)
+    ap.add_argument("--model", default="HCT116_RNA002", choices=sorted(MODELS))
+    ap.add_argument("--cpu-sample-sites", type=int, default=20_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"synthetic {a.sites} DRACH sites x {a.reads} reads, {a.model}, num_iterations={a.iters}, "
+            f"20 reads/bag, site-sharded")
+
+
+def algorithmic_bytes_per_site(n_reads: int) -> int:
+    # features in + k-mer ids + CSR offset + per-read prob out + site_prob + mod_count
+    return n_reads * 36 + 12 + 8 + n_reads * 4 + 8
+
+
+def synth_shard(site_a: int, site_b: int, n_reads: int, seed_tag: int):
+    """Synthetic shard [site_a, site_b): N(0,1) features, uniform valid k-mer ids."""
+    rng = np.random.default_rng([0, seed_tag, site_a])
+    ns = site_b - site_a
+    feats = rng.standard_normal((ns * n_reads, 9), dtype=np.float32)
+    read_off = np.arange(ns + 1, dtype=np.int64) * n_reads
+    kmer = rng.integers(0, 66, size=(ns, 3), dtype=np.int32)
+    return feats, read_off, kmer
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_reference(a):
+    """--impl reference: the reference's CPU path (oracle port; the reference is pure Python and cannot
+    travel to the GPU box) on all host cores, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import ReadEncoderParams
+    from oracle.cpu_baseline import host_cores, time_reference_port
+    params = ReadEncoderParams.from_npz(os.path.join(ROOT, "m6anet_b200", "assets", "model_states", MODELS[a.model][0]))
+    n_sample = min(a.sites, a.cpu_sample_sites)
+    feats, off, kmer = synth_shard(0, n_sample, a.reads, 0)
+    cores = host_cores()
+    for _ in range(min(a.warmup, 1)):
+        time_reference_port(params, feats, off, kmer, a.iters, n_procs=cores, read_threshold=MODELS[a.model][1])
+    times, last = [], None
+    for _ in range(a.steps):
+        t0 = time.perf_counter()
+        last = time_reference_port(params, feats, off, kmer, a.iters, n_procs=cores, read_threshold=MODELS[a.model][1])
+        times.append(n_sample / last["sites_per_s"])
+    t = sum(times)
+    value = n_sample * a.steps / t
+    sample = (f"{n_sample} sites x {a.reads} reads per step (bounded sample of the {a.sites}-site job), "
+              f"encoder={last['t_encoder_s']:.3f}s mc={last['t_mc_s']:.3f}s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sites": a.sites, "reads_per_site": a.reads, "num_iterations": a.iters},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    from m6anet_b200 import weights as W
+    from m6anet_b200.engine import MilEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    # ---- shard: contiguous site ranges, equal read counts (constant n_reads) -------------------------
+    bounds = [a.sites * r // world for r in range(world + 1)]
+    sa, sb = bounds[rank], bounds[rank + 1]
+    ns = sb - sa
+    shard_max = max(bounds[r + 1] - bounds[r] for r in range(world))
+    feats_h, off_h, kmer_h = synth_shard(sa, sb, a.reads, 1)
+    thr = MODELS[a.model][1]
+    eng = MilEngine(W.from_npz(os.path.join(ROOT, "m6anet_b200", "assets", "model_states", MODELS[a.model][0])), dev)
+
+    feats_p = torch.from_numpy(feats_h).pin_memory()
+    off_p = torch.from_numpy(off_h).pin_memory()
+    kmer_p = torch.from_numpy(kmer_h).pin_memory()
+    feats_d, off_d, kmer_d = feats_p.to(dev), off_p.to(dev), kmer_p.to(dev)
+    read_prob = torch.empty(feats_d.shape[0], dtype=torch.float32, device=dev)
+    # site outputs packed [shard_max, 2] (site_prob, mod_count bits) so ONE all-gather moves both
+    site_pack = torch.zeros((shard_max, 2), dtype=torch.float32, device=dev)
+    site_prob = torch.empty(ns, dtype=torch.float32, device=dev)
+    mod_count = torch.empty(ns, dtype=torch.int32, device=dev)
+    gathered = torch.empty((world * shard_max, 2), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step():
+        eng.infer_device(feats_d, off_d, kmer_d, a.iters, seed=0, site_id_base=sa, read_threshold=thr,
+                         out=(read_prob, site_prob, mod_count))
+        if world > 1:
+            site_pack[:ns, 0] = site_prob
+            site_pack[:ns, 1] = mod_count.view(torch.float32)
+            dist.all_gather_into_tensor(gathered, site_pack)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 0)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    ev[0].record()
+    for i in range(a.steps):
+        kev[i][0].record()
+        eng.infer_device(feats_d, off_d, kmer_d, a.iters, seed=0, site_id_base=sa, read_threshold=thr,
+                         out=(read_prob, site_prob, mod_count))
+        kev[i][1].record()
+        if world > 1:
+            site_pack[:ns, 0] = site_prob
+            site_pack[:ns, 1] = mod_count.view(torch.float32)
+            dist.all_gather_into_tensor(gathered, site_pack)
+    ev[1].record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev[0].elapsed_time(ev[1])
+    kernel_ms = [k0.elapsed_time(k1) for k0, k1 in kev]
+    launch = eng.last_launch()
+    if world > 1:
+        t = torch.tensor([elapsed_ms, max(kernel_ms)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t[0])
+    ms_per_step = elapsed_ms / a.steps
+    value = a.sites / (ms_per_step * 1e-3)
+
+    # ---- roofline of the fused kernel (this rank's launches; algorithmic bytes / CUDA-event time) -----
+    peak, peak_src = peaks()
+    k_avg_ms = sum(kernel_ms) / len(kernel_ms)
+    alg_bytes = ns * algorithmic_bytes_per_site(a.reads)
+    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("sites") == a.sites and tj.get("reads") == a.reads:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "mil_infer_kernel", "kernel_ms": k_avg_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "note": "the kernel is fp32-issue bound (>=6.2k FMA per read + 20k samples per site); see DESIGN.md"}
+
+    # ---- e2e: host buffers through the C-ABI host call, H2D + kernel + D2H inside the timed region ------
+    e2e = None
+    if not a.no_e2e:
+        rp_h = torch.empty(feats_h.shape[0], dtype=torch.float32).pin_memory().numpy()
+        sp_h = torch.empty(ns, dtype=torch.float32).pin_memory().numpy()
+        mc_h = torch.empty(ns, dtype=torch.int32).pin_memory().numpy()
+        fp, op_, kp = feats_p.numpy(), off_p.numpy(), kmer_p.numpy()
+        e_steps = max(1, min(a.steps, 5))
+        eng.infer_host(fp, op_, kp, a.iters, seed=0, site_id_base=sa, read_threshold=thr, out=(rp_h, sp_h, mc_h))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            eng.infer_host(fp, op_, kp, a.iters, seed=0, site_id_base=sa, read_threshold=thr, out=(rp_h, sp_h, mc_h))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        # same numbers as the resident path?
+        same = bool(np.array_equal(sp_h, site_prob.cpu().numpy()))
+        e2e = {"value": a.sites * e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(feats_h.nbytes + off_h.nbytes + kmer_h.nbytes) * 1,
+               "d2h_bytes_per_step": int(rp_h.nbytes + sp_h.nbytes + mc_h.nbytes),
+               "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps, "bytes_are": "per rank",
+               "timer": "host perf_counter around the synchronous C-ABI call, max over ranks",
+               "matches_resident_path": same}
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import ReadEncoderParams
+        from oracle.cpu_baseline import host_cores, time_reference_port
+        params = ReadEncoderParams.from_npz(os.path.join(ROOT, "m6anet_b200", "assets", "model_states", MODELS[a.model][0]))
+        n_sample = min(a.sites, a.cpu_sample_sites)
+        r = time_reference_port(params, feats_h[: n_sample * a.reads], off_h[: n_sample + 1], kmer_h[:n_sample], a.iters,
+                                n_procs=host_cores(), read_threshold=thr)
+        cpu = {"value": r["sites_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"first {n_sample} sites of the job ({n_sample * a.reads} reads), encoder {r['t_encoder_s']:.3f}s "
+                         f"+ MC Pool({r['cores']}) {r['t_mc_s']:.3f}s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "sites": a.sites, "reads_per_site": a.reads,
+                       "num_iterations": a.iters, "n_samples": 20, "weights": a.model,
+                       "parallelism": f"site-sharded x{n_gpus}" + (", 1 NCCL all-gather/step" if n_gpus > 1 else ""),
+                       "l2": f"inputs ({feats_h.nbytes / 1e6:.0f} MB/rank) larger than L2" if feats_h.nbytes > 126e6
+                             else "inputs smaller than L2 (not flushed)",
+                       "launch": launch},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": a.steps * launch["n_launches"],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

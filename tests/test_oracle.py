@@ -148,3 +148,15 @@ def test_empty_site_and_single_read():
     rp, sp, mc = mil_inference(params, feats, np.array([0, 0, 1]), np.array([[0, 1, 2], [3, 4, 5]]), n_iters=4)
     assert np.isnan(sp[0]) and mc[0] == 0
     assert np.isclose(sp[1], 1 - (1 - rp[0]) ** 20, atol=1e-6)
+
+
+def test_torch_port_used_for_cpu_timing_equals_numpy_restatement(synthetic_inputs):
+    from oracle.cpu_baseline import read_probabilities_torch
+    si = synthetic_inputs
+    kmer_rows = np.repeat(si["kmer_idx"], np.diff(si["read_off"]), axis=0)
+    for tag in ("HCT116_RNA002", "signal_only"):
+        params = oracle_params(tag)
+        a = read_probabilities(params, si["feats"], kmer_rows)
+        b = read_probabilities_torch(params, si["feats"], kmer_rows)
+        assert np.max(np.abs(a - b)) <= 2e-6
+        assert np.array_equal(b, load_golden(tag)["read_prob"])   # identical calls to the reference => identical bits
