@@ -16,7 +16,7 @@
  *                              mod_ratio                                    (:53)
  *                              calculate_site_proba/_calculate_site_proba   (:54,74-104)
  *   m6a_mil_infer_host_f32  the same, including features.to(device) / probs.cpu()  (:35-36,41)
- *   m6a_philox_indices      np.random.choice index draw                     (:85)
+ *   m6a_sample_indices      np.random.choice index draw                     (:85)
  *
  * Conventions: plain C types only; no exceptions cross the boundary; every function returns an
  * int status (0 = ok, <0 = M6A_E*, >0 = a cudaError_t value) readable with m6a_strerror().
@@ -80,17 +80,18 @@ int m6a_model_destroy(m6a_model_t *model);
  *
  *   feats       [total_reads, 9] float32, normalised, site-contiguous rows (4-byte aligned; a
  *               16-byte aligned base enables the TMA bulk-copy path, otherwise plain loads are used)
- *   read_off    [n_sites + 1] int64 CSR offsets into feats rows; read_off[0] may be > 0
- *               (a shard of a larger buffer); non-decreasing
+ *   read_off    [n_sites + 1] int64 CSR offsets into feats rows, non-decreasing, read_off[0] == 0 and
+ *               read_off[n_sites] == total_reads (a shard passes its own rows and re-based offsets)
  *   kmer_idx    [n_sites, 3] int32 five-mer ids of the site's 7-mer (ignored when emb_dim == 0; may be NULL then)
  *   site_id_base  global id of site 0: the RNG counter is (site_id_base + s), so results do not
  *               depend on how sites are sharded over GPUs
  *   n_samples   reads per bag (the reference hard-codes 20), 1..64
  *   n_iters     Monte-Carlo iterations (>= 1)
- *   seed        Philox key
+ *   seed        Philox key of the index streams
  *   sample_idx  optional [n_sites, n_iters, n_samples] uint16 explicit indices (parity / replay
- *               mode, requires every site to have <= 65535 reads); NULL => on-device Philox4x32-10
- *               with index = (word * n_reads) >> 32
+ *               mode, requires every site to have <= 65535 reads); NULL => on-device stream:
+ *               Philox4x32-10-seeded MWC64X lane streams, index = (word * n_reads) >> 32
+ *               (specification: oracle/philox.py, m6anet_b200/csrc/m6a_rng.cuh)
  *   read_threshold  float32 threshold of mod_ratio (p >= threshold)
  * outputs
  *   read_prob   [total_reads] float32, indexed like feats rows (absolute row index)
@@ -117,7 +118,7 @@ int m6a_mil_infer_host_f32(const m6a_model_t *model, const float *feats, const i
 
 /* Writes the device index stream of one site: out [n_iters, n_samples] int32 (DEVICE pointer).
  * Test hook proving the device generator equals oracle/philox.py bit for bit. */
-int m6a_philox_indices(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters,
+int m6a_sample_indices(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters,
                        int32_t n_samples, int32_t *out, void *stream);
 
 /* Launch geometry of the last m6a_mil_infer_f32 call on this thread (for bench/roofline

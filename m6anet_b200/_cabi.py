@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 EXPORTS = (
     "m6a_version", "m6a_strerror", "m6a_model_create", "m6a_model_destroy", "m6a_mil_infer_f32",
-    "m6a_mil_infer_host_f32", "m6a_philox_indices", "m6a_last_launch",
+    "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_last_launch",
 )
 
 
@@ -71,8 +71,8 @@ def lib() -> C.CDLL:
     L.m6a_mil_infer_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, u64, vp, f32, vp, vp, vp, vp]
     L.m6a_mil_infer_host_f32.restype = C.c_int
     L.m6a_mil_infer_host_f32.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, u64, f32, vp, vp, vp, i32]
-    L.m6a_philox_indices.restype = C.c_int
-    L.m6a_philox_indices.argtypes = [u64, i64, i32, i32, i32, vp, vp]
+    L.m6a_sample_indices.restype = C.c_int
+    L.m6a_sample_indices.argtypes = [u64, i64, i32, i32, i32, vp, vp]
     L.m6a_last_launch.restype = C.c_int
     L.m6a_last_launch.argtypes = [C.POINTER(i32)] * 5
     _lib = L

@@ -59,9 +59,12 @@ extern "C" int m6a_model_create(const m6a_weights_t* w, m6a_model_t** out) {
   WeightImage* img = static_cast<WeightImage*>(calloc(1, sizeof(WeightImage)));
   if (!img) return M6A_ENOMEM;
   for (int j = 0; j < h1; ++j) {
-    for (int k = 0; k < kNSig; ++k) img->l12[j][k] = w->w1[static_cast<size_t>(j) * in1 + k];
-    for (int k = 0; k < kH2; ++k) img->l12[j][kW2Off + k] = w->w2[static_cast<size_t>(k) * h1 + j];
+    float* row = img->pair[j >> 1];
+    const int half = j & 1;
+    for (int k = 0; k < kNSig; ++k) row[2 * k + half] = w->w1[static_cast<size_t>(j) * in1 + k];
+    for (int k = 0; k < kH2; ++k) row[(half ? kW2Off1 : kW2Off0) + k] = w->w2[static_cast<size_t>(k) * h1 + j];
   }
+  img->n_pairs = (h1 + 1) / 2;
   for (int k = 0; k < kH2; ++k) {
     img->b2[k] = w->b2[k];
     img->w3[k] = w->w3[k];
@@ -154,8 +157,7 @@ extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, c
   a.seed = seed;
   a.n_samples = n_samples;
   a.n_iters = n_iters;
-  a.iters_per_lane = (n_iters + 32 * kSlabCap - 1) / (32 * kSlabCap);
-  a.n_slabs = (n_iters + 32 * a.iters_per_lane - 1) / (32 * a.iters_per_lane);
+  block_layout(n_iters, &a.iters_per_lane, &a.n_blocks);
   a.read_threshold = read_threshold;
   a.feats_tma_ok = (reinterpret_cast<uintptr_t>(feats) & 15u) == 0;
 
@@ -167,10 +169,10 @@ extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, c
   return M6A_OK;
 }
 
-extern "C" int m6a_philox_indices(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters, int32_t n_samples,
+extern "C" int m6a_sample_indices(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters, int32_t n_samples,
                                   int32_t* out, void* stream) {
   if (!out || n_reads < 1 || n_iters < 1 || n_samples < 1) return M6A_EINVAL;
-  cudaError_t e = launch_philox_indices(seed, static_cast<uint64_t>(site_id), static_cast<uint32_t>(n_reads), n_iters,
+  cudaError_t e = launch_sample_indices(seed, static_cast<uint64_t>(site_id), static_cast<uint32_t>(n_reads), n_iters,
                                         n_samples, out, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? M6A_OK : static_cast<int>(e);
 }

@@ -9,30 +9,33 @@
 // Work decomposition (one persistent CTA loops over tiles; a tile = G consecutive sites):
 //   stage   the tile's feature rows are one contiguous byte range of `feats` -> one cp.async.bulk
 //           (TMA, mbarrier completion) per chunk of kChunkReads rows into shared memory
-//   phase A thread-per-read (kReadsPerThread reads per thread): h1-step fused loop
-//             h_j = relu(c_site[j] + w1[j,0:9].x);  acc[0:32] += w2[:,j] * h_j
-//           weights are read from shared memory at warp-uniform addresses (LDS.128 broadcast);
+//   phase A thread-per-read (kReadsPerThread reads per thread), hidden units two at a time with
+//           packed FFMA2 (B200 issues FFMA2 at half the FFMA rate but each does two FMAs, which
+//           frees issue slots for the integer work of phase B running in the co-resident CTA):
+//             (h_j0,h_j1) = relu(c_site[j0:j1] + sum_k (w1[j0,k],w1[j1,k]) * x_k)     9 FFMA2
+//             acc[0:32]  += w2[:,j0] * h_j0 ; acc[0:32] += w2[:,j1] * h_j1            32 FFMA2
+//           weights come from shared memory at warp-uniform addresses (LDS.128 broadcast);
 //           the k-mer embedding part of Linear-1 is a per-site constant c_site (m6a_layout.h)
-//   phase B warp-per-(site, slab of 32 iterations): every lane runs one MC iteration: 5 Philox4x32-10
-//           calls -> 20 indices -> product of q[idx] from shared memory; butterfly reduce per slab
-//   final   ordered sum of slab partials / n_iters -> site_prob
-// The summation order is a function of n_iters only (not of tiling, grid or GPU count), so a site's
-// result is bit-identical however the sites are sharded.
+//   phase B warp-per-(site, block of 32*ipl iterations): every lane owns a Philox-seeded MWC64X
+//           stream (m6a_rng.cuh) and runs its ipl iterations: 20 x (draw, mulhi, LDS q[idx], FMUL)
+//   final   butterfly sum per block, ordered sum of block partials / n_iters -> site_prob
+// The summation order and the index streams are functions of (seed, site id, n_iters) only -- not of
+// tiling, grid or GPU count -- so a site's result is bit-identical however the sites are sharded.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 
 #include "m6a_kernel.h"
-#include "m6a_philox.cuh"
+#include "m6a_rng.cuh"
 
 namespace m6a {
 
 struct Smem {
   WeightImage w;
   alignas(16) float feat[kChunkReads * kNSig + 8];  // + unaligned head (<=3 floats) + tail round-up
-  float csite[kSitesPerTileMax][kCStride];
+  alignas(16) float csite[kSitesPerTileMax][kCStride];
   float q[kQCap];
-  float partial[kSitesPerTileMax][kSlabCap];
+  float partial[kSitesPerTileMax][kMaxBlocks];
   int roff[kSitesPerTileMax + 1];
   int cnt[kSitesPerTileMax];
   int kid[kSitesPerTileMax][kKmerPos];
@@ -76,68 +79,42 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   } while (!done);
 }
 
-// ---- one Monte-Carlo iteration: 1 - prod_{s<n_samples} q[idx_s] ---------------------------------
-template <int NS>
-__device__ __forceinline__ float mc_iteration_philox(const float* __restrict__ qs, uint32_t n, uint32_t it,
-                                                     uint32_t site_lo, uint32_t site_hi, uint32_t k0,
-                                                     uint32_t k1, int n_samples_rt) {
-  const int ns = NS > 0 ? NS : n_samples_rt;
-  float prod = 1.0f;
-  if (NS > 0) {
-#pragma unroll
-    for (int c = 0; c < (NS + 3) / 4; ++c) {
-      const Philox4 r = philox4x32_10(static_cast<uint32_t>(c), it, site_lo, site_hi, k0, k1);
-      if (4 * c + 0 < NS) prod *= qs[__umulhi(r.x, n)];
-      if (4 * c + 1 < NS) prod *= qs[__umulhi(r.y, n)];
-      if (4 * c + 2 < NS) prod *= qs[__umulhi(r.z, n)];
-      if (4 * c + 3 < NS) prod *= qs[__umulhi(r.w, n)];
-    }
-  } else {
-    for (int c = 0; 4 * c < ns; ++c) {
-      const Philox4 r = philox4x32_10(static_cast<uint32_t>(c), it, site_lo, site_hi, k0, k1);
-      prod *= qs[__umulhi(r.x, n)];
-      if (4 * c + 1 < ns) prod *= qs[__umulhi(r.y, n)];
-      if (4 * c + 2 < ns) prod *= qs[__umulhi(r.z, n)];
-      if (4 * c + 3 < ns) prod *= qs[__umulhi(r.w, n)];
-    }
-  }
-  return 1.0f - prod;
-}
-
-// q read back from global read_prob (tile too large for the shared q table)
-template <bool kFromProb>
-__device__ __forceinline__ float q_at(const float* base, uint32_t i) {
-  return kFromProb ? 1.0f - base[i] : base[i];
-}
-
-__device__ __forceinline__ float mc_iteration_generic(const float* qbase, bool from_prob, uint32_t n, uint32_t it,
-                                                      uint32_t site_lo, uint32_t site_hi, uint32_t k0, uint32_t k1,
-                                                      int ns, const uint16_t* __restrict__ explicit_idx) {
-  float prod = 1.0f;
-  if (explicit_idx != nullptr) {
-    for (int s = 0; s < ns; ++s) {
-      const uint32_t i = explicit_idx[s];
-      prod *= from_prob ? q_at<true>(qbase, i) : q_at<false>(qbase, i);
-    }
-  } else {
-    for (int c = 0; 4 * c < ns; ++c) {
-      const Philox4 r = philox4x32_10(static_cast<uint32_t>(c), it, site_lo, site_hi, k0, k1);
-      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (4 * c + u < ns) {
-          const uint32_t i = __umulhi(w[u], n);
-          prod *= from_prob ? q_at<true>(qbase, i) : q_at<false>(qbase, i);
-        }
-      }
-    }
-  }
-  return 1.0f - prod;
+__device__ __forceinline__ float2 ffma2(float2 a, float b, float2 c) {
+  return __ffma2_rn(a, make_float2(b, b), c);   // SASS: FFMA2 Rd, Ra.F32x2.HI_LO, Rb.F32, Rc.F32x2.HI_LO
 }
 
 __device__ __forceinline__ float warp_butterfly_sum(float v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// ---- one lane's share of a (site, block): ipl iterations of 1 - prod_{s<n_samples} q[idx_s] ------
+template <int NS>
+__device__ __forceinline__ float mc_lane_smem(const float* __restrict__ qs, uint32_t n, Mwc64x& g, int rounds) {
+  float v = 0.0f;
+  for (int k = 0; k < rounds; ++k) {
+    float prod = 1.0f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) prod *= qs[__umulhi(g.next(), n)];
+    v += 1.0f - prod;
+  }
+  return v;
+}
+
+// generic path: any n_samples, q from shared memory or 1 - read_prob from global, optional explicit indices
+__device__ __forceinline__ float mc_lane_generic(const float* qbase, bool from_prob, uint32_t n, Mwc64x& g, int rounds,
+                                                 int ns, const uint16_t* __restrict__ explicit_idx,
+                                                 size_t explicit_round_stride) {
+  float v = 0.0f;
+  for (int k = 0; k < rounds; ++k) {
+    float prod = 1.0f;
+    for (int s = 0; s < ns; ++s) {
+      const uint32_t i = explicit_idx != nullptr ? explicit_idx[k * explicit_round_stride + s] : __umulhi(g.next(), n);
+      prod *= from_prob ? 1.0f - qbase[i] : qbase[i];
+    }
+    v += 1.0f - prod;
+  }
   return v;
 }
 
@@ -165,11 +142,10 @@ mil_infer_kernel(const KernelArgs a) {
   uint32_t f_parity = 0;
   bool weights_ready = false;
 
-  const int h1 = a.model.h1;
-  const uint32_t k0 = static_cast<uint32_t>(a.seed), k1 = static_cast<uint32_t>(a.seed >> 32);
-  const int n_slabs = a.n_slabs, ipl = a.iters_per_lane;
+  const int n_pairs = (a.model.h1 + 1) >> 1;
+  const int n_blocks = a.n_blocks, ipl = a.iters_per_lane;
   const bool tma_ok = a.feats_tma_ok;
-  const float inv_iters_den = static_cast<float>(a.n_iters);
+  const float n_iters_f = static_cast<float>(a.n_iters);
 
   for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const long long s0 = tile * a.sites_per_tile;
@@ -192,51 +168,37 @@ mil_infer_kernel(const KernelArgs a) {
     const bool q_in_smem = nr <= kQCap;
     const int n_chunks = (nr + kChunkReads - 1) / kChunkReads;
 
-    // ---- stage chunk 0 (TMA) while c_site is being computed --------------------------------------
-    auto stage_chunk = [&](int chunk) {
-      // rows [ra, rb) of feats -> sm.feat[head + i*9 + k]
+    // ---- feature staging: rows [ra, ra+rows) of feats -> sm.feat[head + i*9 + k] ---------------------
+    auto chunk_span = [&](int chunk, unsigned long long& b0, unsigned long long& b1, unsigned long long& g0,
+                          unsigned long long& g1) {
       const long long ra = r0 + static_cast<long long>(chunk) * kChunkReads;
       const int rows = min(kChunkReads, nr - chunk * kChunkReads);
-      const unsigned long long b0 = static_cast<unsigned long long>(ra) * (kNSig * 4);
-      const unsigned long long b1 = b0 + static_cast<unsigned long long>(rows) * (kNSig * 4);
+      b0 = static_cast<unsigned long long>(ra) * (kNSig * 4);
+      b1 = b0 + static_cast<unsigned long long>(rows) * (kNSig * 4);
+      g0 = b0 & ~15ull;                                   // 16-byte granules for the bulk copy
+      g1 = (b1 + 15ull) & ~15ull;
+      const unsigned long long gend = a.feats_bytes & ~15ull;
+      if (g1 > gend) g1 = gend;
+    };
+    auto stage_chunk = [&](int chunk) {
+      unsigned long long b0, b1, g0, g1;
+      chunk_span(chunk, b0, b1, g0, g1);
       if (tma_ok) {
-        const unsigned long long g0 = b0 & ~15ull;
-        unsigned long long g1 = (b1 + 15ull) & ~15ull;
-        const unsigned long long gend = a.feats_bytes & ~15ull;
-        if (g1 > gend) g1 = gend;
         if (tid == 0 && g1 > g0) {
           mbar_expect_tx(&sm.bar_f, static_cast<uint32_t>(g1 - g0));
           bulk_g2s(sm.feat, reinterpret_cast<const unsigned char*>(a.feats) + g0, static_cast<uint32_t>(g1 - g0),
                    &sm.bar_f);
         }
-        // bytes past the last 16-byte granule of the buffer (only the very last chunk can have them)
-        if (b1 > g1) {
-          const int nf = static_cast<int>((b1 - max(g1, b0)) >> 2);
+        if (b1 > g1) {  // bytes past the last full 16-byte granule of the buffer (very last chunk only)
           const unsigned long long src0 = max(g1, b0);
+          const int nf = static_cast<int>((b1 - src0) >> 2);
           if (tid < nf) sm.feat[((src0 - g0) >> 2) + tid] = a.feats[(src0 >> 2) + tid];
         }
       } else {
-        const int nf = rows * kNSig;
-        const float* src = a.feats + ra * kNSig;
+        const int nf = static_cast<int>((b1 - b0) >> 2);
+        const float* src = a.feats + (b0 >> 2);
         for (int i = tid; i < nf; i += kThreads) sm.feat[i] = src[i];
       }
-    };
-    auto chunk_has_tma = [&](int chunk) -> bool {
-      if (!tma_ok) return false;
-      const long long ra = r0 + static_cast<long long>(chunk) * kChunkReads;
-      const int rows = min(kChunkReads, nr - chunk * kChunkReads);
-      const unsigned long long b0 = static_cast<unsigned long long>(ra) * (kNSig * 4);
-      const unsigned long long b1 = b0 + static_cast<unsigned long long>(rows) * (kNSig * 4);
-      unsigned long long g1 = (b1 + 15ull) & ~15ull;
-      const unsigned long long gend = a.feats_bytes & ~15ull;
-      if (g1 > gend) g1 = gend;
-      return g1 > (b0 & ~15ull);
-    };
-    auto chunk_head = [&](int chunk) -> int {
-      if (!tma_ok) return 0;
-      const unsigned long long b0 =
-          static_cast<unsigned long long>(r0 + static_cast<long long>(chunk) * kChunkReads) * (kNSig * 4);
-      return static_cast<int>((b0 & 15ull) >> 2);
     };
 
     if (n_chunks > 0) stage_chunk(0);
@@ -247,10 +209,9 @@ mil_infer_kernel(const KernelArgs a) {
       const size_t tstride = static_cast<size_t>(a.model.n_kmer) * kH1Max;
       for (int i = tid; i < ns * kH1Max; i += kThreads) {
         const int s = i / kH1Max, j = i - s * kH1Max;
-        const float c = __ldg(ctab + static_cast<size_t>(sm.kid[s][0]) * kH1Max + j) +
-                        __ldg(ctab + tstride + static_cast<size_t>(sm.kid[s][1]) * kH1Max + j) +
-                        __ldg(ctab + 2 * tstride + static_cast<size_t>(sm.kid[s][2]) * kH1Max + j);
-        sm.csite[s][j] = c;
+        sm.csite[s][j] = __ldg(ctab + static_cast<size_t>(sm.kid[s][0]) * kH1Max + j) +
+                         __ldg(ctab + tstride + static_cast<size_t>(sm.kid[s][1]) * kH1Max + j) +
+                         __ldg(ctab + 2 * tstride + static_cast<size_t>(sm.kid[s][2]) * kH1Max + j);
       }
     }
     if (!weights_ready) {
@@ -260,12 +221,14 @@ mil_infer_kernel(const KernelArgs a) {
 
     // ---- phase A: read encoder ---------------------------------------------------------------------
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
-      if (chunk_has_tma(chunk)) {
+      unsigned long long b0, b1, g0, g1;
+      chunk_span(chunk, b0, b1, g0, g1);
+      if (tma_ok && g1 > g0) {
         mbar_wait(&sm.bar_f, f_parity);
         f_parity ^= 1u;
       }
       __syncthreads();  // plain-load staging + csite visible
-      const int head = chunk_head(chunk);
+      const int head = tma_ok ? static_cast<int>((b0 - g0) >> 2) : 0;
       const int cbase = chunk * kChunkReads;
 
       float x[kReadsPerThread][kNSig];
@@ -291,40 +254,47 @@ mil_infer_kernel(const KernelArgs a) {
       __syncthreads();  // feature buffer free again
       if (chunk + 1 < n_chunks) stage_chunk(chunk + 1);   // overlaps the MLP below
 
-      float acc[kReadsPerThread][kH2];
+      float2 acc[kReadsPerThread][kH2 / 2];
 #pragma unroll
       for (int r = 0; r < kReadsPerThread; ++r)
 #pragma unroll
-        for (int k = 0; k < kH2; ++k) acc[r][k] = sm.w.b2[k];
+        for (int k = 0; k < kH2 / 2; ++k) acc[r][k] = make_float2(sm.w.b2[2 * k], sm.w.b2[2 * k + 1]);
 
-#pragma unroll 2
-      for (int j = 0; j < h1; ++j) {
-        const float4* wj = reinterpret_cast<const float4*>(sm.w.l12[j]);
-        const float4 wa = wj[0], wb = wj[1], wc = wj[2];
-        float h[kReadsPerThread];
+#pragma unroll 1
+      for (int p = 0; p < n_pairs; ++p) {
+        const float4* wp = reinterpret_cast<const float4*>(sm.w.pair[p]);
+        const float4 u0 = wp[0], u1 = wp[1], u2 = wp[2], u3 = wp[3], u4 = wp[4];
+        float2 h[kReadsPerThread];
 #pragma unroll
         for (int r = 0; r < kReadsPerThread; ++r) {
-          float t = cs[r][j];
-          t = fmaf(wa.x, x[r][0], t);
-          t = fmaf(wa.y, x[r][1], t);
-          t = fmaf(wa.z, x[r][2], t);
-          t = fmaf(wa.w, x[r][3], t);
-          t = fmaf(wb.x, x[r][4], t);
-          t = fmaf(wb.y, x[r][5], t);
-          t = fmaf(wb.z, x[r][6], t);
-          t = fmaf(wb.w, x[r][7], t);
-          t = fmaf(wc.x, x[r][8], t);
-          h[r] = fmaxf(t, 0.0f);
+          float2 t = *reinterpret_cast<const float2*>(cs[r] + 2 * p);
+          t = ffma2(make_float2(u0.x, u0.y), x[r][0], t);
+          t = ffma2(make_float2(u0.z, u0.w), x[r][1], t);
+          t = ffma2(make_float2(u1.x, u1.y), x[r][2], t);
+          t = ffma2(make_float2(u1.z, u1.w), x[r][3], t);
+          t = ffma2(make_float2(u2.x, u2.y), x[r][4], t);
+          t = ffma2(make_float2(u2.z, u2.w), x[r][5], t);
+          t = ffma2(make_float2(u3.x, u3.y), x[r][6], t);
+          t = ffma2(make_float2(u3.z, u3.w), x[r][7], t);
+          t = ffma2(make_float2(u4.x, u4.y), x[r][8], t);
+          h[r] = make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f));
         }
 #pragma unroll
         for (int k4 = 0; k4 < kH2 / 4; ++k4) {
-          const float4 w = wj[kW2Off / 4 + k4];
+          const float4 w = wp[kW2Off0 / 4 + k4];
 #pragma unroll
           for (int r = 0; r < kReadsPerThread; ++r) {
-            acc[r][4 * k4 + 0] = fmaf(w.x, h[r], acc[r][4 * k4 + 0]);
-            acc[r][4 * k4 + 1] = fmaf(w.y, h[r], acc[r][4 * k4 + 1]);
-            acc[r][4 * k4 + 2] = fmaf(w.z, h[r], acc[r][4 * k4 + 2]);
-            acc[r][4 * k4 + 3] = fmaf(w.w, h[r], acc[r][4 * k4 + 3]);
+            acc[r][2 * k4 + 0] = ffma2(make_float2(w.x, w.y), h[r].x, acc[r][2 * k4 + 0]);
+            acc[r][2 * k4 + 1] = ffma2(make_float2(w.z, w.w), h[r].x, acc[r][2 * k4 + 1]);
+          }
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < kH2 / 4; ++k4) {
+          const float4 w = wp[kW2Off1 / 4 + k4];
+#pragma unroll
+          for (int r = 0; r < kReadsPerThread; ++r) {
+            acc[r][2 * k4 + 0] = ffma2(make_float2(w.x, w.y), h[r].y, acc[r][2 * k4 + 0]);
+            acc[r][2 * k4 + 1] = ffma2(make_float2(w.z, w.w), h[r].y, acc[r][2 * k4 + 1]);
           }
         }
       }
@@ -333,7 +303,10 @@ mil_infer_kernel(const KernelArgs a) {
       for (int r = 0; r < kReadsPerThread; ++r) {
         float z = sm.w.b3;
 #pragma unroll
-        for (int k = 0; k < kH2; ++k) z = fmaf(sm.w.w3[k], fmaxf(acc[r][k], 0.0f), z);
+        for (int k = 0; k < kH2 / 2; ++k) {
+          z = fmaf(sm.w.w3[2 * k], fmaxf(acc[r][k].x, 0.0f), z);
+          z = fmaf(sm.w.w3[2 * k + 1], fmaxf(acc[r][k].y, 0.0f), z);
+        }
         const float p = 1.0f / (1.0f + expf(-z));
         if (valid[r]) {
           const int lr = cbase + r * kThreads + tid;
@@ -347,34 +320,32 @@ mil_infer_kernel(const KernelArgs a) {
 
     // ---- phase B: Monte-Carlo noisy-OR ----------------------------------------------------------
     {
-      const int items = ns * n_slabs;
+      const int items = ns * n_blocks;
       for (int item = warp; item < items; item += kWarps) {
-        const int sl = item / n_slabs, slab = item - sl * n_slabs;
+        const int sl = item / n_blocks, blk = item - sl * n_blocks;
         const int n = sm.roff[sl + 1] - sm.roff[sl];
         float v = 0.0f;
         if (n > 0) {
-          const unsigned long long gsite = static_cast<unsigned long long>(a.site_id_base + s0 + sl);
-          const uint32_t site_lo = static_cast<uint32_t>(gsite), site_hi = static_cast<uint32_t>(gsite >> 32);
-          for (int jj = 0; jj < ipl; ++jj) {
-            const long long it = (static_cast<long long>(slab) * ipl + jj) * 32 + lane;
-            if (it < a.n_iters) {
-              if (NS > 0 && q_in_smem && a.sample_idx == nullptr) {
-                v += mc_iteration_philox<NS>(sm.q + sm.roff[sl], static_cast<uint32_t>(n), static_cast<uint32_t>(it),
-                                             site_lo, site_hi, k0, k1, a.n_samples);
-              } else {
-                const float* qbase = q_in_smem ? (sm.q + sm.roff[sl]) : (a.read_prob + r0 + sm.roff[sl]);
-                const uint16_t* ex =
-                    a.sample_idx != nullptr
-                        ? a.sample_idx + (static_cast<size_t>(s0 + sl) * a.n_iters + it) * a.n_samples
-                        : nullptr;
-                v += mc_iteration_generic(qbase, !q_in_smem, static_cast<uint32_t>(n), static_cast<uint32_t>(it),
-                                          site_lo, site_hi, k0, k1, a.n_samples, ex);
-              }
-            }
+          // this lane's iterations: it = (blk*ipl + k)*32 + lane, k < ipl, it < n_iters
+          const long long it0 = static_cast<long long>(blk) * ipl * 32 + lane;
+          long long left = (static_cast<long long>(a.n_iters) - it0 + 31) / 32;   // rounds with it < n_iters
+          const int rounds = static_cast<int>(left < 0 ? 0 : (left > ipl ? ipl : left));
+          Mwc64x g;
+          g.seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk),
+                 static_cast<unsigned long long>(a.site_id_base + s0 + sl), a.seed);
+          if (NS > 0 && q_in_smem && a.sample_idx == nullptr) {
+            v = mc_lane_smem<NS>(sm.q + sm.roff[sl], static_cast<uint32_t>(n), g, rounds);
+          } else {
+            const float* qbase = q_in_smem ? (sm.q + sm.roff[sl]) : (a.read_prob + r0 + sm.roff[sl]);
+            const uint16_t* ex = a.sample_idx != nullptr
+                                     ? a.sample_idx + (static_cast<size_t>(s0 + sl) * a.n_iters + it0) * a.n_samples
+                                     : nullptr;
+            v = mc_lane_generic(qbase, !q_in_smem, static_cast<uint32_t>(n), g, rounds, a.n_samples, ex,
+                                static_cast<size_t>(32) * a.n_samples);
           }
         }
         v = warp_butterfly_sum(v);
-        if (lane == 0) sm.partial[sl][slab] = v;
+        if (lane == 0) sm.partial[sl][blk] = v;
       }
     }
     __syncthreads();
@@ -383,8 +354,8 @@ mil_infer_kernel(const KernelArgs a) {
     if (tid < ns) {
       const int n = sm.roff[tid + 1] - sm.roff[tid];
       float s = 0.0f;
-      for (int k = 0; k < n_slabs; ++k) s += sm.partial[tid][k];
-      a.site_prob[s0 + tid] = n > 0 ? s / inv_iters_den : __int_as_float(0x7fc00000);
+      for (int k = 0; k < n_blocks; ++k) s += sm.partial[tid][k];
+      a.site_prob[s0 + tid] = n > 0 ? s / n_iters_f : __int_as_float(0x7fc00000);
       a.mod_count[s0 + tid] = sm.cnt[tid];
     }
     __syncthreads();  // roff/cnt/partial are rewritten by the next tile
@@ -393,19 +364,18 @@ mil_infer_kernel(const KernelArgs a) {
   if (!weights_ready) mbar_wait(&sm.bar_w, 0);  // never leave with a bulk copy in flight
 }
 
-__global__ void philox_indices_kernel(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
-                                      int32_t* __restrict__ out) {
-  const int n_calls = (n_samples + 3) / 4;
-  const long long total = static_cast<long long>(n_iters) * n_calls;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int it = static_cast<int>(i / n_calls), c = static_cast<int>(i - static_cast<long long>(it) * n_calls);
-    const Philox4 r = philox4x32_10(static_cast<uint32_t>(c), static_cast<uint32_t>(it), static_cast<uint32_t>(site_id),
-                                    static_cast<uint32_t>(site_id >> 32), static_cast<uint32_t>(seed),
-                                    static_cast<uint32_t>(seed >> 32));
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-    for (int u = 0; u < 4; ++u)
-      if (4 * c + u < n_samples) out[static_cast<long long>(it) * n_samples + 4 * c + u] = __umulhi(w[u], n_reads);
+__global__ void sample_indices_kernel(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
+                                      int n_blocks, int ipl, int32_t* __restrict__ out) {
+  // one thread per (block, lane) stream, exactly the order phase B consumes it
+  const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+  if (stream >= n_blocks * 32) return;
+  const int blk = stream >> 5, lane = stream & 31;
+  Mwc64x g;
+  g.seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk), site_id, seed);
+  for (int k = 0; k < ipl; ++k) {
+    const long long it = (static_cast<long long>(blk) * ipl + k) * 32 + lane;
+    if (it >= n_iters) break;
+    for (int s = 0; s < n_samples; ++s) out[it * n_samples + s] = static_cast<int32_t>(__umulhi(g.next(), n_reads));
   }
 }
 
@@ -444,9 +414,13 @@ cudaError_t launch_mil_infer(const KernelArgs& a, int n_sms, cudaStream_t stream
   return cudaGetLastError();
 }
 
-cudaError_t launch_philox_indices(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
+cudaError_t launch_sample_indices(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
                                   int32_t* out, cudaStream_t stream) {
-  philox_indices_kernel<<<64, 256, 0, stream>>>(seed, site_id, n_reads, n_iters, n_samples, out);
+  int ipl, n_blocks;
+  block_layout(n_iters, &ipl, &n_blocks);
+  const int streams = n_blocks * 32;
+  sample_indices_kernel<<<(streams + 127) / 128, 128, 0, stream>>>(seed, site_id, n_reads, n_iters, n_samples,
+                                                                  n_blocks, ipl, out);
   return cudaGetLastError();
 }
 

@@ -14,8 +14,17 @@ constexpr int kReadsPerThread = 2;
 constexpr int kChunkReads = kThreads * kReadsPerThread;  // feature rows staged per bulk copy
 constexpr int kSitesPerTileMax = 32;
 constexpr int kQCap = 4096;             // q = 1-p entries kept in shared memory per tile
-constexpr int kSlabCap = 64;            // Monte-Carlo partial sums per site
-constexpr int kCStride = kH1Max + 1;    // odd stride: per-lane site rows hit distinct banks
+constexpr int kCStride = kH1Max;        // even (float2 loads); 152 mod 32 = 24 keeps neighbouring site rows on distinct banks
+constexpr int kMcMaxBlocks = 64;        // == kMaxBlocks in m6a_rng.cuh: Monte-Carlo partial sums per site
+constexpr int kMcMinItersPerLane = 8;
+
+// Decomposition of a site's iterations into blocks of 32*ipl (oracle/philox.py: block_layout).
+inline void block_layout(int n_iters, int* ipl, int* n_blocks) {
+  int v = (n_iters + 32 * kMcMaxBlocks - 1) / (32 * kMcMaxBlocks);
+  if (v < kMcMinItersPerLane) v = kMcMinItersPerLane;
+  *ipl = v;
+  *n_blocks = (n_iters + 32 * v - 1) / (32 * v);
+}
 
 struct KernelArgs {
   DeviceModel model;
@@ -34,8 +43,8 @@ struct KernelArgs {
   int sites_per_tile;
   int n_samples;
   int n_iters;
-  int n_slabs;         // ceil(n_iters / (32 * iters_per_lane)) <= kSlabCap
-  int iters_per_lane;  // ceil(n_iters / (32 * kSlabCap))
+  int n_blocks;        // ceil(n_iters / (32 * iters_per_lane)) <= 64
+  int iters_per_lane;  // max(8, ceil(n_iters / 2048))
   float read_threshold;
   bool feats_tma_ok;   // feats base 16-byte aligned -> cp.async.bulk staging
 };
@@ -46,7 +55,7 @@ struct LaunchInfo {
 
 size_t smem_bytes();
 cudaError_t launch_mil_infer(const KernelArgs& a, int n_sms, cudaStream_t stream, LaunchInfo* info);
-cudaError_t launch_philox_indices(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
+cudaError_t launch_sample_indices(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
                                   int32_t* out, cudaStream_t stream);
 
 }  // namespace m6a

@@ -8,20 +8,25 @@ constexpr int kNSig = 9;          // signal features per read (reference model_b
 constexpr int kH2 = 32;           // second Linear width (reference m6anet.toml: output_channel = 32)
 constexpr int kH1Max = 152;       // first Linear width limit (shipped: 150)
 constexpr int kKmerPos = 3;       // five-mers per site (centre + 1 flank each side)
-constexpr int kRowFloats = 44;    // per hidden unit j: w1[j,0..8], 3 pad, w2[0..31, j]
-constexpr int kW2Off = 12;
+constexpr int kPairs = kH1Max / 2; // hidden units are processed two at a time (packed FFMA2)
+constexpr int kPairFloats = 84;    // per pair p=(j0,j1): 9 x (w1[j0,k], w1[j1,k]), 2 pad, w2[0..31,j0], w2[0..31,j1]
+constexpr int kW2Off0 = 20;        // float offset of w2[:, j0]
+constexpr int kW2Off1 = 52;        // float offset of w2[:, j1]
 
 // Image of the read-encoder weights as the kernel wants them in shared memory.  One
-// cp.async.bulk moves it.  Per hidden unit j the 9 signal weights of Linear-1 (BatchNorm folded)
-// sit next to column j of Linear-2, so the fused j-loop reads 11 consecutive float4 at a
-// warp-uniform address (LDS.128 broadcast).
+// cp.async.bulk moves it.  Hidden units go in pairs (j0, j1) = (2p, 2p+1): the 9 signal weights of
+// Linear-1 (BatchNorm folded) are interleaved as float2 (w1[j0,k], w1[j1,k]) so that one FFMA2 with
+// the scalar x_k updates (h_j0, h_j1); columns j0 and j1 of Linear-2 follow as 2 x 16 float2 so that
+// one FFMA2 with the scalar h_j updates two outputs.  The pair loop reads 21 consecutive float4 at a
+// warp-uniform address (LDS.128 broadcast).  h1 odd => the last pair's j1 half is zero.
 struct alignas(16) WeightImage {
-  float l12[kH1Max][kRowFloats];  // 26,752 B
+  float pair[kPairs][kPairFloats];  // 25,536 B
   float b2[kH2];
   float w3[kH2];
   float b3;
   int32_t h1;
-  int32_t pad[2];
+  int32_t n_pairs;
+  int32_t pad;
 };
 static_assert(sizeof(WeightImage) % 16 == 0, "bulk copy size must be a multiple of 16");
 

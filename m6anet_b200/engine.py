@@ -112,13 +112,13 @@ class MilEngine:
         _cabi.check(rc, "m6a_mil_infer_host_f32")
         return read_prob, site_prob, mod_count
 
-    def philox_indices(self, seed: int, site_id: int, n_reads: int, n_iters: int, n_samples: int = DEFAULT_N_SAMPLES):
+    def sample_indices(self, seed: int, site_id: int, n_reads: int, n_iters: int, n_samples: int = DEFAULT_N_SAMPLES):
         torch = self._torch
         out = torch.empty((n_iters, n_samples), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            rc = self._lib.m6a_philox_indices(seed & 0xFFFFFFFFFFFFFFFF, site_id, n_reads, n_iters, n_samples,
+            rc = self._lib.m6a_sample_indices(seed & 0xFFFFFFFFFFFFFFFF, site_id, n_reads, n_iters, n_samples,
                                               out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
-        _cabi.check(rc, "m6a_philox_indices")
+        _cabi.check(rc, "m6a_sample_indices")
         return out
 
     def last_launch(self) -> dict:

@@ -14,9 +14,10 @@ Parity status: PINNED.  ``tests/test_oracle.py`` checks the restatement against
      mod_ratio, site probabilities; copied as fixtures under ``tests/golden/bundled``),
  (b) outputs of the unmodified reference imported from ``/root/reference`` in the build
      container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``),
- (c) Random123 known-answer vectors for Philox4x32-10.
+ (c) Random123 known-answer vectors for Philox4x32-10 and D. B. Thomas' MWC64X recurrence.
 """
-from .philox import philox4x32_10, sample_indices, sample_indices_mt19937  # noqa: F401
+from .philox import (philox4x32_10, sample_indices, sample_indices_many, sample_indices_mt19937,  # noqa: F401
+                     block_layout)
 from .mil_oracle import (  # noqa: F401
     ReadEncoderParams,
     read_probabilities,

@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .philox import sample_indices
+from .philox import sample_indices_many
 
 
 @dataclass
@@ -114,7 +114,7 @@ def mil_inference(params: ReadEncoderParams, feats: np.ndarray, read_off: np.nda
     Follows ``run_inference`` (utils/inference_utils.py:35-54): read encoder over every read,
     ``group_results`` split by n_reads (:107-140), ``mod_ratio`` (:53), MC noisy-OR (:54,74-87).
     Index stream: ``sample_idx[s]`` if given, else the Philox stream of site
-    ``site_id_base + s`` (oracle/philox.py).
+    ``site_id_base + s`` (oracle/philox.py: Philox-seeded MWC64X lane streams).
 
     Returns (read_prob f32 [total_reads], site_prob f32 [n_sites], mod_count i32 [n_sites]).
     """
@@ -128,12 +128,18 @@ def mil_inference(params: ReadEncoderParams, feats: np.ndarray, read_off: np.nda
     site_prob = np.zeros(n_sites, dtype=np.float32)
     mod_count = np.zeros(n_sites, dtype=np.int32)
     thr = np.float32(read_threshold)
-    for s in range(n_sites):
-        p = read_prob[read_off[s]:read_off[s + 1]]
-        mod_count[s] = int(np.count_nonzero(p >= thr))
-        if len(p) == 0:
-            site_prob[s] = np.float32("nan")
-            continue
-        idx = sample_idx[s] if sample_idx is not None else sample_indices(seed, site_id_base + s, len(p), n_iters, n_samples)
-        site_prob[s] = noisy_or_site_probability(p, idx)
+    CH = 64  # sites per vectorised index-stream batch
+    for s0 in range(0, n_sites, CH):
+        s1 = min(n_sites, s0 + CH)
+        idx_b = None
+        if sample_idx is None:
+            idx_b = sample_indices_many(seed, site_id_base + np.arange(s0, s1), np.maximum(n_reads[s0:s1], 1), n_iters, n_samples)
+        for s in range(s0, s1):
+            p = read_prob[read_off[s]:read_off[s + 1]]
+            mod_count[s] = int(np.count_nonzero(p >= thr))
+            if len(p) == 0:
+                site_prob[s] = np.float32("nan")
+                continue
+            idx = sample_idx[s] if sample_idx is not None else idx_b[s - s0]
+            site_prob[s] = noisy_or_site_probability(p, idx)
     return read_prob, site_prob, mod_count

@@ -6,13 +6,30 @@ from the process-global MT19937 stream, inside a freshly forked ``Pool`` (ibid. 
 the reference's own output is not reproducible run to run.  Parity on
 ``probability_modified`` is therefore defined on a SHARED index stream.  Two streams exist:
 
-* ``sample_indices`` -- the product's device stream: Philox4x32-10 (Salmon et al., SC'11;
-  the generator behind cuRAND/PyTorch CUDA), counter-based so that the draw for
-  (seed, global site id, iteration, sample) does not depend on GPU count or tiling.
-  This file is its NumPy restatement; ``m6anet_b200/csrc/m6a_philox.cuh`` is the device copy.
+* ``sample_indices`` -- the product's device stream (specification below); this file is its
+  NumPy restatement, ``m6anet_b200/csrc/m6a_rng.cuh`` the device copy; the two are compared
+  bit for bit on the GPU (tests/test_gpu_parity.py::test_device_index_stream_matches_oracle).
 * ``sample_indices_mt19937`` -- a replay of the reference's legacy ``np.random`` stream for
   ONE site drawn right after ``np.random.seed`` (usable through the kernel's explicit-index
   mode).
+
+Device stream specification ("Philox-seeded MWC64X lane streams")
+-----------------------------------------------------------------
+A site's iterations are cut into blocks of ``32 * ipl`` iterations,
+``ipl = max(8, ceil(n_iters / 2048))`` (so at most 64 blocks).  Iteration ``it`` belongs to
+block ``b = it // (32*ipl)``, lane ``l = it % 32`` and is that lane's round ``k = (it // 32) % ipl``.
+Every (site, block, lane) owns an independent generator:
+
+  seeding   (w0, w1, _, _) = Philox4x32-10(ctr = (l, b, site_id & 0xffffffff, site_id >> 32),
+                                           key = (seed & 0xffffffff, seed >> 32))
+            x = w0;  c = (w1 * (A - 1)) >> 32;  if x == c == 0: x = 1          (A = 4294883355)
+  draw      word = x ^ c;  t = A * x + c (64 bit);  x = t & 0xffffffff;  c = t >> 32     (MWC64X, D. B. Thomas 2011)
+  index     (word * n_reads) >> 32                                   (bias <= n_reads / 2**32)
+
+and draws, in order, the ``n_samples`` indices of its round 0, then round 1, ... .  Philox4x32-10
+(Salmon et al., SC'11; the cuRAND / PyTorch-CUDA generator) gives key/counter separation, so a
+site's stream does not depend on GPU count, sharding or tiling; the multiply-with-carry stream
+costs one wide multiply per draw on the device instead of twenty.
 """
 from __future__ import annotations
 
@@ -22,8 +39,11 @@ PHILOX_M0 = np.uint64(0xD2511F53)
 PHILOX_M1 = np.uint64(0xCD9E8D57)
 PHILOX_W0 = 0x9E3779B9
 PHILOX_W1 = 0xBB67AE85
+MWC_A = 4294883355
 _MASK32 = np.uint64(0xFFFFFFFF)
 _SHIFT32 = np.uint64(32)
+MAX_BLOCKS = 64
+MIN_ITERS_PER_LANE = 8
 
 
 def philox4x32_10(ctr, key):
@@ -53,26 +73,49 @@ def philox4x32_10(ctr, key):
     return out.astype(np.uint32)
 
 
-def sample_indices(seed: int, site_id: int, n_reads: int, n_iters: int, n_samples: int = 20):
-    """Device index stream for one site -> int64 [n_iters, n_samples] in [0, n_reads).
+def iters_per_lane(n_iters: int) -> int:
+    return max(MIN_ITERS_PER_LANE, -(-int(n_iters) // (32 * MAX_BLOCKS)))
 
-    Specification (mirrored by the CUDA kernel):
-      key   = (seed & 0xffffffff, seed >> 32)
-      ctr   = (call, iteration, site_id & 0xffffffff, site_id >> 32),  call = sample // 4
-      word  = philox4x32_10(ctr, key)[sample % 4]
-      index = (word * n_reads) >> 32            (multiply-shift; bias <= n_reads / 2**32)
-    """
+
+def block_layout(n_iters: int):
+    """(ipl, n_blocks) of the device decomposition of a site's iterations."""
+    ipl = iters_per_lane(n_iters)
+    return ipl, -(-int(n_iters) // (32 * ipl))
+
+
+def sample_indices_many(seed: int, site_ids, n_reads, n_iters: int, n_samples: int = 20) -> np.ndarray:
+    """Device index stream for several sites -> int64 [n_sites, n_iters, n_samples]."""
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    site_id = int(site_id) & 0xFFFFFFFFFFFFFFFF
-    n_calls = (n_samples + 3) // 4
-    ctr = np.empty((n_iters, n_calls, 4), dtype=np.uint32)
-    ctr[..., 0] = np.arange(n_calls, dtype=np.uint32)[None, :]
-    ctr[..., 1] = np.arange(n_iters, dtype=np.uint32)[:, None]
-    ctr[..., 2] = site_id & 0xFFFFFFFF
-    ctr[..., 3] = site_id >> 32
+    site_ids = np.asarray(site_ids, dtype=np.uint64).reshape(-1)
+    n_reads = np.asarray(n_reads, dtype=np.uint64).reshape(-1)
+    S = len(site_ids)
+    ipl, n_blocks = block_layout(n_iters)
+    ctr = np.empty((S, n_blocks, 32, 4), dtype=np.uint32)
+    ctr[..., 0] = np.arange(32, dtype=np.uint32)[None, None, :]
+    ctr[..., 1] = np.arange(n_blocks, dtype=np.uint32)[None, :, None]
+    ctr[..., 2] = (site_ids & _MASK32).astype(np.uint32)[:, None, None]
+    ctr[..., 3] = (site_ids >> _SHIFT32).astype(np.uint32)[:, None, None]
     key = np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint32)
-    words = philox4x32_10(ctr, key).reshape(n_iters, n_calls * 4)[:, :n_samples]
-    return ((words.astype(np.uint64) * np.uint64(n_reads)) >> _SHIFT32).astype(np.int64)
+    w = philox4x32_10(ctr, key)
+    x = w[..., 0].astype(np.uint64)
+    c = (w[..., 1].astype(np.uint64) * np.uint64(MWC_A - 1)) >> _SHIFT32
+    x = np.where((x == 0) & (c == 0), np.uint64(1), x)
+    A = np.uint64(MWC_A)
+    # out laid out [S, block, round, lane, sample] == iteration-major after reshape
+    out = np.empty((S, n_blocks, ipl, 32, n_samples), dtype=np.int64)
+    nr = n_reads[:, None, None]
+    for k in range(ipl):
+        for s in range(n_samples):
+            word = x ^ c
+            out[:, :, k, :, s] = ((word * nr) >> _SHIFT32).astype(np.int64)
+            t = A * x + c
+            x, c = t & _MASK32, t >> _SHIFT32
+    return out.reshape(S, n_blocks * ipl * 32, n_samples)[:, :n_iters, :]
+
+
+def sample_indices(seed: int, site_id: int, n_reads: int, n_iters: int, n_samples: int = 20) -> np.ndarray:
+    """Device index stream for one site -> int64 [n_iters, n_samples] in [0, n_reads)."""
+    return sample_indices_many(seed, [int(site_id) & 0xFFFFFFFFFFFFFFFF], [n_reads], n_iters, n_samples)[0]
 
 
 def sample_indices_mt19937(seed: int, n_reads: int, n_iters: int, n_samples: int = 20):

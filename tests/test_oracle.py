@@ -10,7 +10,8 @@ import pytest
 
 from conftest import ALL_TAGS, load_golden, oracle_params
 from oracle import (closed_form_site_probability, mil_inference, mod_ratio, noisy_or_site_probability,
-                    philox4x32_10, read_probabilities, sample_indices, sample_indices_mt19937)
+                    philox4x32_10, read_probabilities, sample_indices, sample_indices_many, sample_indices_mt19937,
+                    block_layout)
 
 
 def test_philox_known_answers():
@@ -32,10 +33,42 @@ def test_sample_indices_range_and_determinism():
     c = sample_indices(5, 2**33 + 4, 37, 64, 20)
     assert a.shape == (64, 20) and a.min() >= 0 and a.max() < 37
     assert np.array_equal(a, b) and not np.array_equal(a, c)
-    # iteration i does not depend on n_iters (counter-based)
-    assert np.array_equal(sample_indices(5, 9, 37, 8, 20), sample_indices(5, 9, 37, 64, 20)[:8])
-    # n_samples not a multiple of 4 is a prefix of the 4-word calls
-    assert np.array_equal(sample_indices(5, 9, 37, 8, 7), sample_indices(5, 9, 37, 8, 8)[:, :7])
+    # iteration i does not depend on n_iters while the block layout is the same (n_iters <= 2048)
+    assert np.array_equal(sample_indices(5, 9, 37, 8, 20), sample_indices(5, 9, 37, 2048, 20)[:8])
+    assert block_layout(1000) == (8, 4) and block_layout(2048) == (8, 8) and block_layout(10000) == (8, 40)
+    assert block_layout(16384) == (8, 64) and block_layout(16385) == (9, 57) and block_layout(1) == (8, 1)
+    # the first round of every lane is the first n_samples draws of its generator
+    assert np.array_equal(sample_indices(5, 9, 37, 32, 7), sample_indices(5, 9, 37, 32, 8)[:, :7])
+    # vectorised == per-site
+    many = sample_indices_many(5, [9, 2**33 + 3], [37, 41], 300, 20)
+    assert np.array_equal(many[0], sample_indices(5, 9, 37, 300, 20))
+    assert np.array_equal(many[1], sample_indices(5, 2**33 + 3, 41, 300, 20))
+
+
+def test_mwc64x_recurrence_matches_reference_formulation():
+    """The uint64 form t = A*x + c used by the oracle equals D. B. Thomas' 32-bit formulation
+    (hi = mul_hi(x, A); x = x*A + c; c = hi + (x < c)) for random states."""
+    rng = np.random.default_rng(0)
+    A = 4294883355
+    for _ in range(2000):
+        x, c = int(rng.integers(0, 2**32)), int(rng.integers(0, A))
+        t = A * x + c
+        hi = (x * A) >> 32
+        x2 = (x * A + c) & 0xFFFFFFFF
+        c2 = hi + (1 if x2 < c else 0)
+        assert (t & 0xFFFFFFFF, t >> 32) == (x2, c2)
+
+
+def test_sample_indices_lanes_and_rounds_are_uncorrelated():
+    idx = sample_indices(3, 77, 1000, 2048, 20).astype(np.float64)
+    per_iter = idx.mean(axis=1)
+    lanes = per_iter.reshape(-1, 32)                   # [round, lane]
+    cc = np.corrcoef(lanes.T)                            # lane x lane over rounds
+    off = cc[~np.eye(32, dtype=bool)]
+    assert np.abs(off).max() < 0.5 and abs(off.mean()) < 0.05
+    x = idx.ravel()
+    r1 = np.corrcoef(x[:-1], x[1:])[0, 1]                # serial correlation of consecutive draws
+    assert abs(r1) < 0.02
 
 
 def test_sample_indices_uniform():
