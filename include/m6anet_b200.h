@@ -110,6 +110,8 @@ int m6a_mil_infer_f32(const m6a_model_t *model, const float *feats, const int64_
  * `n_chunks` read-balanced chunks (0 => automatic) that are copied, scored and copied back on
  * rotating CUDA streams so that H2D, kernel and D2H overlap.  Synchronous.  Pinned host buffers
  * overlap best; pageable ones still work.  sample_idx is not supported on this path.
+ * The model handle keeps a grow-only device workspace (3 pipeline slots) for this call, so steady-state
+ * calls allocate nothing; concurrent host calls on one model are serialised.
  */
 int m6a_mil_infer_host_f32(const m6a_model_t *model, const float *feats, const int64_t *read_off,
                            const int32_t *kmer_idx, int64_t n_sites, int64_t site_id_base,

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -12,13 +13,25 @@
 
 using namespace m6a;
 
+constexpr int kHostSlots = 3;
+struct HostSlot {   // one stage of the host-buffer pipeline (m6a_mil_infer_host_f32)
+  cudaStream_t stream = nullptr;
+  void *d_feats = nullptr, *d_off = nullptr, *d_kmer = nullptr, *d_rp = nullptr, *d_sp = nullptr, *d_mc = nullptr;
+  size_t cap_feats = 0, cap_off = 0, cap_kmer = 0, cap_rp = 0, cap_sp = 0, cap_mc = 0;
+  int64_t* h_off = nullptr;   // pinned staging for re-based offsets
+  size_t cap_hoff = 0;
+};
+
 struct m6a_model {
   DeviceModel dev;
   void* d_image;
   void* d_ctab;
   int device;
   int n_sms;
+  HostSlot slots[kHostSlots];
+  std::mutex ws_mutex;
 };
+void m6a_release_workspace(m6a_model* m);
 
 static thread_local LaunchInfo g_last = {0, 0, 0, 0};
 static thread_local int g_last_launches = 0;
@@ -114,6 +127,7 @@ extern "C" int m6a_model_create(const m6a_weights_t* w, m6a_model_t** out) {
 
 extern "C" int m6a_model_destroy(m6a_model_t* model) {
   if (!model) return M6A_OK;
+  m6a_release_workspace(model);
   cudaFree(model->d_image);
   cudaFree(model->d_ctab);
   delete model;
@@ -188,23 +202,60 @@ extern "C" int m6a_last_launch(int32_t* grid, int32_t* block, int32_t* smem_byte
 }
 
 // ---- host-buffer path: chunked, stream-pipelined H2D -> kernel -> D2H --------------------------------
-namespace {
-struct Slot {
-  cudaStream_t stream = nullptr;
-  float* d_feats = nullptr;
-  int64_t* d_off = nullptr;
-  int32_t* d_kmer = nullptr;
-  float* d_rp = nullptr;
-  float* d_sp = nullptr;
-  int32_t* d_mc = nullptr;
-  int64_t* h_off = nullptr;  // pinned staging for re-based offsets
-};
-}  // namespace
+// The pipeline owns a small persistent workspace inside the model handle (3 slots of device buffers, one
+// stream each, pinned staging for the re-based CSR offsets).  It only grows, so steady-state calls do no
+// allocation at all; m6a_model_destroy releases it.
+static cudaError_t ensure_bytes(void** p, size_t* cap, size_t need) {
+  if (need <= *cap) return cudaSuccess;
+  if (*p) {
+    cudaError_t e = cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    if (e != cudaSuccess) return e;
+  }
+  const size_t want = need + need / 8 + 256;
+  cudaError_t e = cudaMalloc(p, want);
+  if (e == cudaSuccess) *cap = want;
+  return e;
+}
 
-extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model, const float* feats, const int64_t* read_off,
+static cudaError_t slot_reserve(HostSlot& sl, int64_t max_sites, int64_t max_reads) {
+  cudaError_t e = cudaSuccess;
+  if (!sl.stream) e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = ensure_bytes(&sl.d_feats, &sl.cap_feats, static_cast<size_t>(max_reads) * kNSig * sizeof(float) + 16);
+  if (e == cudaSuccess) e = ensure_bytes(&sl.d_rp, &sl.cap_rp, static_cast<size_t>(max_reads) * sizeof(float) + 16);
+  if (e == cudaSuccess) e = ensure_bytes(&sl.d_off, &sl.cap_off, static_cast<size_t>(max_sites + 1) * sizeof(int64_t));
+  if (e == cudaSuccess) e = ensure_bytes(&sl.d_kmer, &sl.cap_kmer, static_cast<size_t>(max_sites) * kKmerPos * sizeof(int32_t));
+  if (e == cudaSuccess) e = ensure_bytes(&sl.d_sp, &sl.cap_sp, static_cast<size_t>(max_sites) * sizeof(float));
+  if (e == cudaSuccess) e = ensure_bytes(&sl.d_mc, &sl.cap_mc, static_cast<size_t>(max_sites) * sizeof(int32_t));
+  if (e == cudaSuccess && static_cast<size_t>(max_sites + 1) > sl.cap_hoff) {
+    if (sl.h_off) cudaFreeHost(sl.h_off);
+    sl.h_off = nullptr;
+    sl.cap_hoff = 0;
+    const size_t want = static_cast<size_t>(max_sites + 1) + static_cast<size_t>(max_sites) / 8 + 16;
+    e = cudaMallocHost(reinterpret_cast<void**>(&sl.h_off), want * sizeof(int64_t));
+    if (e == cudaSuccess) sl.cap_hoff = want;
+  }
+  return e;
+}
+
+void m6a_release_workspace(m6a_model* m) {
+  for (int s = 0; s < kHostSlots; ++s) {
+    HostSlot& sl = m->slots[s];
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    cudaFree(sl.d_feats); cudaFree(sl.d_off); cudaFree(sl.d_kmer);
+    cudaFree(sl.d_rp); cudaFree(sl.d_sp); cudaFree(sl.d_mc);
+    if (sl.h_off) cudaFreeHost(sl.h_off);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+    sl = HostSlot();
+  }
+}
+
+extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model_c, const float* feats, const int64_t* read_off,
                                       const int32_t* kmer_idx, int64_t n_sites, int64_t site_id_base,
                                       int32_t n_samples, int32_t n_iters, uint64_t seed, float read_threshold,
                                       float* read_prob, float* site_prob, int32_t* mod_count, int32_t n_chunks) {
+  m6a_model* model = const_cast<m6a_model*>(model_c);
   if (!model || n_sites < 0) return M6A_EINVAL;
   if (n_sites == 0) return M6A_OK;
   if (!read_off || !site_prob || !mod_count) return M6A_EINVAL;
@@ -213,11 +264,12 @@ extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model, const float* fea
   if (total_reads < 0) return M6A_EINVAL;
   if (total_reads > 0 && (!feats || !read_prob)) return M6A_EINVAL;
   if (model->dev.emb_dim > 0 && !kmer_idx) return M6A_EINVAL;
+  if (n_samples < 1 || n_samples > 64 || n_iters < 1) return M6A_EINVAL;
 
-  // chunk boundaries: balanced by reads, cut at site boundaries
+  // chunk boundaries: balanced by reads, cut at site boundaries (~32 MB of features per chunk by default)
   if (n_chunks <= 0) {
     const int64_t bytes = total_reads * kNSig * 4;
-    n_chunks = static_cast<int>(std::min<int64_t>(64, std::max<int64_t>(1, bytes / (64ll << 20))));
+    n_chunks = static_cast<int>(std::min<int64_t>(256, std::max<int64_t>(1, bytes / (32ll << 20))));
     if (n_chunks > 1 && n_chunks < 4) n_chunks = 4;
   }
   if (n_chunks > n_sites) n_chunks = static_cast<int>(n_sites);
@@ -234,71 +286,47 @@ extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model, const float* fea
     max_reads = std::max(max_reads, read_off[cut[c + 1]] - read_off[cut[c]]);
   }
 
-  const int n_slots = std::min(3, n_chunks);
-  Slot slots[3];
-  int rc = M6A_OK;
-  auto cleanup = [&]() {
-    for (int s = 0; s < n_slots; ++s) {
-      Slot& sl = slots[s];
-      if (sl.stream) cudaStreamSynchronize(sl.stream);
-      cudaFree(sl.d_feats); cudaFree(sl.d_off); cudaFree(sl.d_kmer);
-      cudaFree(sl.d_rp); cudaFree(sl.d_sp); cudaFree(sl.d_mc);
-      if (sl.h_off) cudaFreeHost(sl.h_off);
-      if (sl.stream) cudaStreamDestroy(sl.stream);
-    }
-  };
-#define M6A_TRY(expr)                       \
-  do {                                      \
-    cudaError_t _e = (expr);                \
-    if (_e != cudaSuccess) {                \
-      rc = static_cast<int>(_e);            \
-      cleanup();                            \
-      return rc;                            \
-    }                                       \
-  } while (0)
-
-  for (int s = 0; s < n_slots; ++s) {
-    Slot& sl = slots[s];
-    M6A_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-    M6A_TRY(cudaMalloc(&sl.d_feats, std::max<int64_t>(1, max_reads) * kNSig * sizeof(float)));
-    M6A_TRY(cudaMalloc(&sl.d_off, (max_sites + 1) * sizeof(int64_t)));
-    M6A_TRY(cudaMalloc(&sl.d_kmer, max_sites * kKmerPos * sizeof(int32_t)));
-    M6A_TRY(cudaMalloc(&sl.d_rp, std::max<int64_t>(1, max_reads) * sizeof(float)));
-    M6A_TRY(cudaMalloc(&sl.d_sp, max_sites * sizeof(float)));
-    M6A_TRY(cudaMalloc(&sl.d_mc, max_sites * sizeof(int32_t)));
-    M6A_TRY(cudaMallocHost(&sl.h_off, (max_sites + 1) * sizeof(int64_t)));
-  }
+  std::lock_guard<std::mutex> guard(model->ws_mutex);
+  const int n_slots = std::min(kHostSlots, n_chunks);
+  for (int s = 0; s < n_slots; ++s) M6A_CUDA(slot_reserve(model->slots[s], max_sites, std::max<int64_t>(1, max_reads)));
 
   int launches = 0;
-  for (int c = 0; c < n_chunks; ++c) {
-    Slot& sl = slots[c % n_slots];
+  int rc = M6A_OK;
+  for (int c = 0; c < n_chunks && rc == M6A_OK; ++c) {
+    HostSlot& sl = model->slots[c % n_slots];
     const int64_t sa = cut[c], sb = cut[c + 1], ns = sb - sa;
     if (ns == 0) continue;
     const int64_t ra = read_off[sa], nr = read_off[sb] - ra;
-    M6A_TRY(cudaStreamSynchronize(sl.stream));  // slot (and its pinned offset staging) free again
-    for (int64_t i = 0; i <= ns; ++i) sl.h_off[i] = read_off[sa + i] - ra;
-    M6A_TRY(cudaMemcpyAsync(sl.d_off, sl.h_off, (ns + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sl.stream));
-    if (nr > 0)
-      M6A_TRY(cudaMemcpyAsync(sl.d_feats, feats + ra * kNSig, nr * kNSig * sizeof(float), cudaMemcpyHostToDevice,
-                              sl.stream));
-    if (kmer_idx)
-      M6A_TRY(cudaMemcpyAsync(sl.d_kmer, kmer_idx + sa * kKmerPos, ns * kKmerPos * sizeof(int32_t),
-                              cudaMemcpyHostToDevice, sl.stream));
-    rc = m6a_mil_infer_f32(model, sl.d_feats, sl.d_off, kmer_idx ? sl.d_kmer : nullptr, ns, nr, site_id_base + sa,
-                           n_samples, n_iters, seed, nullptr, read_threshold, sl.d_rp, sl.d_sp, sl.d_mc, sl.stream);
-    if (rc != M6A_OK) {
-      cleanup();
-      return rc;
+    cudaError_t e = cudaStreamSynchronize(sl.stream);  // slot (and its pinned offset staging) free again
+    if (e == cudaSuccess) {
+      for (int64_t i = 0; i <= ns; ++i) sl.h_off[i] = read_off[sa + i] - ra;
+      e = cudaMemcpyAsync(sl.d_off, sl.h_off, (ns + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sl.stream);
     }
+    if (e == cudaSuccess && nr > 0)
+      e = cudaMemcpyAsync(sl.d_feats, feats + ra * kNSig, nr * kNSig * sizeof(float), cudaMemcpyHostToDevice, sl.stream);
+    if (e == cudaSuccess && kmer_idx)
+      e = cudaMemcpyAsync(sl.d_kmer, kmer_idx + sa * kKmerPos, ns * kKmerPos * sizeof(int32_t), cudaMemcpyHostToDevice,
+                          sl.stream);
+    if (e != cudaSuccess) {
+      rc = static_cast<int>(e);
+      break;
+    }
+    rc = m6a_mil_infer_f32(model, static_cast<const float*>(sl.d_feats), static_cast<const int64_t*>(sl.d_off),
+                           kmer_idx ? static_cast<const int32_t*>(sl.d_kmer) : nullptr, ns, nr, site_id_base + sa,
+                           n_samples, n_iters, seed, nullptr, read_threshold, static_cast<float*>(sl.d_rp),
+                           static_cast<float*>(sl.d_sp), static_cast<int32_t*>(sl.d_mc), sl.stream);
+    if (rc != M6A_OK) break;
     ++launches;
-    if (nr > 0)
-      M6A_TRY(cudaMemcpyAsync(read_prob + ra, sl.d_rp, nr * sizeof(float), cudaMemcpyDeviceToHost, sl.stream));
-    M6A_TRY(cudaMemcpyAsync(site_prob + sa, sl.d_sp, ns * sizeof(float), cudaMemcpyDeviceToHost, sl.stream));
-    M6A_TRY(cudaMemcpyAsync(mod_count + sa, sl.d_mc, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+    if (nr > 0) e = cudaMemcpyAsync(read_prob + ra, sl.d_rp, nr * sizeof(float), cudaMemcpyDeviceToHost, sl.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(site_prob + sa, sl.d_sp, ns * sizeof(float), cudaMemcpyDeviceToHost, sl.stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(mod_count + sa, sl.d_mc, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream);
+    if (e != cudaSuccess) rc = static_cast<int>(e);
   }
-  for (int s = 0; s < n_slots; ++s) M6A_TRY(cudaStreamSynchronize(slots[s].stream));
-  cleanup();
+  for (int s = 0; s < n_slots; ++s) {
+    cudaError_t e = cudaStreamSynchronize(model->slots[s].stream);
+    if (e != cudaSuccess && rc == M6A_OK) rc = static_cast<int>(e);
+  }
   g_last_launches = launches;
-  return M6A_OK;
-#undef M6A_TRY
+  return rc;
 }

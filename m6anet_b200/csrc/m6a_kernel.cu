@@ -90,13 +90,23 @@ __device__ __forceinline__ float warp_butterfly_sum(float v) {
 }
 
 // ---- one lane's share of a (site, block): ipl iterations of 1 - prod_{s<n_samples} q[idx_s] ------
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 template <int NS>
 __device__ __forceinline__ float mc_lane_smem(const float* __restrict__ qs, uint32_t n, Mwc64x& g, int rounds) {
+  const uint32_t qaddr = smem_u32(qs);     // shared-space byte address of the site's q table
   float v = 0.0f;
   for (int k = 0; k < rounds; ++k) {
     float prod = 1.0f;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) prod *= qs[__umulhi(g.next(), n)];
+    for (int s = 0; s < NS; ++s) {
+      const uint32_t idx = __umulhi(g.next(), n);
+      prod *= lds_f32(qaddr + (idx << 2));   // IMAD.HI, LEA, LDS, FMUL
+    }
     v += 1.0f - prod;
   }
   return v;

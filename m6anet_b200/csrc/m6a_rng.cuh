@@ -56,9 +56,15 @@ struct Mwc64x {
   }
   __device__ __forceinline__ uint32_t next() {
     const uint32_t word = x ^ c;
-    const uint64_t t = static_cast<uint64_t>(kMwcA) * x + c;   // one IMAD.WIDE.U32 with 64-bit addend
-    x = static_cast<uint32_t>(t);
-    c = static_cast<uint32_t>(t >> 32);
+    // (c:x) = A * x + c as one wide multiply (FMA pipe) plus an add-with-carry pair (ALU pipe).  The
+    // fused form IMAD.WIDE Rd, x, A, (c,0) needs the addend in an aligned register pair, which costs
+    // two extra moves per draw on the FMA pipe.
+    uint32_t lo, hi;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(kMwcA));
+    uint32_t nx, nc;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(nx), "=r"(nc) : "r"(lo), "r"(c), "r"(hi));
+    x = nx;
+    c = nc;
     return word;
   }
 };
