@@ -1,0 +1,62 @@
+"""Site sharding over ranks and the single collective of the path.
+
+Sites are independent, so a job is cut into contiguous global site ranges balanced by cumulative read
+count; rank r scores sites [bounds[r], bounds[r+1]) with site_id_base = bounds[r], which makes the
+result independent of the number of ranks.  The only exchange is one all-gather of the per-site outputs
+(site_prob float32 + mod_count int32 = 8 bytes per site, packed into one tensor).
+Backend: NCCL for CUDA tensors, gloo for the CPU tests of this logic.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Tuple
+
+import numpy as np
+
+
+def env_world() -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from the torchrun environment (1 process per GPU)."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_bounds(n_reads: np.ndarray, world_size: int) -> List[int]:
+    """Contiguous site ranges with (nearly) equal total reads.  Returns world_size + 1 site indices."""
+    n_reads = np.asarray(n_reads, dtype=np.int64)
+    n_sites = len(n_reads)
+    if world_size <= 1 or n_sites == 0:
+        return [0] + [n_sites] * max(1, world_size)
+    cum = np.cumsum(n_reads)
+    total = int(cum[-1])
+    bounds = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        b = int(np.searchsorted(cum, target, side="left")) + 1     # first prefix reaching the target
+        if b > 0 and b <= n_sites and abs(cum[b - 1] - target) > abs((cum[b - 2] if b >= 2 else 0) - target):
+            b -= 1
+        bounds.append(min(max(b, bounds[-1]), n_sites))
+    bounds.append(n_sites)
+    return bounds
+
+
+def all_gather_site_outputs(site_prob, mod_count, bounds: List[int], group=None):
+    """One all-gather of every rank's (site_prob, mod_count) -> full-length tensors on every rank.
+
+    site_prob float32 [n_local], mod_count int32 [n_local] (torch tensors, CUDA for NCCL / CPU for gloo).
+    Shards are padded to the longest shard and packed as [max_shard, 2] float32 words so that a single
+    collective moves both outputs; mod_count travels bit-cast, not converted."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
+    assert site_prob.numel() == sizes[rank] == mod_count.numel()
+    m = max(max(sizes), 1)
+    pack = torch.zeros((m, 2), dtype=torch.float32, device=site_prob.device)
+    pack[: sizes[rank], 0] = site_prob
+    pack[: sizes[rank], 1] = mod_count.view(torch.float32)
+    out = torch.empty((world * m, 2), dtype=torch.float32, device=site_prob.device)
+    dist.all_gather_into_tensor(out, pack, group=group)
+    out = out.view(world, m, 2)
+    sp = torch.cat([out[r, : sizes[r], 0] for r in range(world)])
+    mc = torch.cat([out[r, : sizes[r], 1].contiguous().view(torch.int32) for r in range(world)])
+    return sp, mc

@@ -1,0 +1,248 @@
+"""`m6anet inference` on the B200 kernel: argparser(), main(args), run_inference(model, dl, args).
+
+Drop-in mirror of reference m6anet/scripts/inference.py (argparser :20-67, main :70-106) and
+m6anet/utils/inference_utils.py (run_inference :14-71, group_results :107-140): same flags, same
+pretrained-model resolution, same inputs (data.info/data.json) and the same two outputs
+    data.site_proba.csv   transcript_id,transcript_position,n_reads,probability_modified,kmer,mod_ratio
+    data.indiv_proba.csv  transcript_id,transcript_position,read_index,probability_modified
+with the reference's row formats ('%s,%d,%s,%.16f,%s,%.16f' / '%s,%d,%s,%.16f', inference_utils.py:59-67).
+
+Differences, all deliberate (SURVEY.md section 3.1 "do not reproduce"):
+  * every site is written (the reference's `if (it + 1) % save_per_batch` flush drops trailing batches);
+  * the Monte-Carlo stream is the counter-based device stream keyed by (--seed, global site index), so two
+    runs -- on any number of GPUs -- give identical files (the reference forks an unseeded Pool per flush);
+  * single-directory read_index is written as an integer (the reference prints the float "966210.0");
+  * --device defaults to "cuda": the hot path has no CPU implementation here and refuses "cpu".
+Under torchrun (WORLD_SIZE > 1) sites are sharded by read count over the ranks, each rank scores its
+shard, one all-gather collects the per-site outputs and the shard files are concatenated in site order.
+"""
+from __future__ import annotations
+
+import multiprocessing
+import os
+import pathlib
+import shutil
+import warnings
+from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
+from concurrent.futures import ProcessPoolExecutor
+from typing import List, Optional
+
+import numpy as np
+
+from .constants import (DEFAULT_MIN_READS, DEFAULT_MODEL_CONFIG, DEFAULT_NORM_PATH, DEFAULT_PRETRAINED_MODEL,
+                        DEFAULT_PRETRAINED_MODELS, DEFAULT_READ_THRESHOLD, PRETRAINED_CONFIGS)
+from .data import NanopolishDS, NanopolishReplicateDS, SiteBatch
+from .dist import all_gather_site_outputs, env_world, shard_bounds
+from .model import MILModel, load_model_config
+
+SITE_HEADER = 'transcript_id,transcript_position,n_reads,probability_modified,kmer,mod_ratio\n'
+INDIV_HEADER = 'transcript_id,transcript_position,read_index,probability_modified\n'
+N_SAMPLES = 20                       # the literal 20 of reference utils/inference_utils.py:54
+DEFAULT_READS_PER_BATCH = 2_000_000  # ingest/score/write granularity (72 MB of features)
+
+
+def argparser():
+    parser = ArgumentParser(formatter_class=ArgumentDefaultsHelpFormatter, add_help=False)
+    # Required arguments
+    parser.add_argument("--input_dir", nargs="*", help='directories containing data.info and data.json.', required=True)
+    parser.add_argument("--out_dir", help='directory to output inference results.', required=True)
+    # Optional arguments (reference scripts/inference.py:33-66)
+    parser.add_argument("--pretrained_model",
+                        help="pre-trained model available at m6anet. Options include {}.".format(DEFAULT_PRETRAINED_MODELS),
+                        default=DEFAULT_PRETRAINED_MODEL, type=str)
+    parser.add_argument("--model_config", help='path to model config file.', default=DEFAULT_MODEL_CONFIG)
+    parser.add_argument("--model_state_dict", help='path to model weights.', default=None)
+    parser.add_argument("--norm_path", help='path to normalization factors file', default=DEFAULT_NORM_PATH)
+    parser.add_argument("--batch_size", help='batch size for inference (sites per reference batch; kept for '
+                        'compatibility, the kernel batches by --reads_per_batch).', default=16, type=int)
+    parser.add_argument("--save_per_batch", help='saving inference results every save_per_batch multiples '
+                        '(kept for compatibility; every site is always written).', default=2, type=int)
+    parser.add_argument("--n_processes", help='number of processes to run (JSON ingest workers).', default=25, type=int)
+    parser.add_argument("--num_iterations", help='number of sampling run.', default=1000, type=int)
+    parser.add_argument("--device", help='device to perform inference with (cuda or cuda:N).', default='cuda', type=str)
+    parser.add_argument("--seed", help='random seed for sampling.', default=0, type=int)
+    parser.add_argument("--read_proba_threshold",
+                        help='default probability threshold for a read to be considered modified.',
+                        default=DEFAULT_READ_THRESHOLD, type=float)
+    # m6anet_b200 extension
+    parser.add_argument("--reads_per_batch", help='reads ingested, scored and written per step.',
+                        default=DEFAULT_READS_PER_BATCH, type=int)
+    return parser
+
+
+# ---- CSV emit ------------------------------------------------------------------------------------------
+def write_site_rows(f, batch: SiteBatch, site_prob: np.ndarray, mod_count: np.ndarray):
+    n_reads = np.diff(batch.read_off)
+    mod_ratio = mod_count.astype(np.float64) / np.maximum(n_reads, 1)      # np.mean(x >= thr) in float64 (:53)
+    out = []
+    for tx, pos, n, sp, kmer, mr in zip(batch.tx_ids, batch.tx_pos, n_reads, site_prob.astype(np.float64), batch.kmers, mod_ratio):
+        out.append('%s,%d,%s,%.16f,%s,%.16f\n' % (tx, pos, n, sp, kmer, mr))
+    f.write("".join(out))
+
+
+def write_indiv_rows(g, batch: SiteBatch, read_prob: np.ndarray):
+    n_reads = np.diff(batch.read_off)
+    tx = np.repeat(batch.tx_ids, n_reads)
+    pos = np.repeat(batch.tx_pos, n_reads)
+    out = []
+    for t, p, rid, rp in zip(tx, pos, batch.read_ids, read_prob.astype(np.float64)):
+        out.append('%s,%d,%s,%.16f\n' % (t, p, rid, rp))
+    g.write("".join(out))
+
+
+# ---- ingest helpers ----------------------------------------------------------------------------------------
+_WORKER_DS = None
+
+
+def _worker_init(ds):
+    global _WORKER_DS
+    _WORKER_DS = ds
+
+
+def _worker_load(span):
+    return _WORKER_DS.load_sites(*span)
+
+
+def _concat_batches(parts: List[SiteBatch]) -> SiteBatch:
+    if len(parts) == 1:
+        return parts[0]
+    offs, base = [np.zeros(1, np.int64)], 0
+    for p in parts:
+        offs.append(p.read_off[1:] + base)
+        base += int(p.read_off[-1])
+    return SiteBatch(np.concatenate([p.feats for p in parts]), np.concatenate(offs), np.concatenate([p.kmer_idx for p in parts]),
+                     np.concatenate([p.read_ids for p in parts]), np.concatenate([p.tx_ids for p in parts]),
+                     np.concatenate([p.tx_pos for p in parts]), np.concatenate([p.kmers for p in parts]))
+
+
+def plan_batches(n_reads: np.ndarray, lo: int, hi: int, reads_per_batch: int) -> List[tuple]:
+    """Cut sites [lo, hi) into consecutive spans of about reads_per_batch reads."""
+    spans, a, acc = [], lo, 0
+    for s in range(lo, hi):
+        acc += int(n_reads[s])
+        if acc >= reads_per_batch:
+            spans.append((a, s + 1))
+            a, acc = s + 1, 0
+    if a < hi:
+        spans.append((a, hi))
+    return spans
+
+
+def _resolve_device(device: str, local_rank: int, world: int):
+    import torch
+    if str(device).startswith("cpu"):
+        raise RuntimeError("m6anet_b200 runs the inference hot path only on CUDA devices (sm_100a); there is no CPU path. "
+                           "Use --device cuda, or the reference implementation for CPU inference.")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device is visible; m6anet_b200 has no CPU fallback")
+    dev = torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", local_rank if world > 1 else torch.cuda.current_device())
+    return dev
+
+
+def run_inference(model: MILModel, dl, args):
+    """Score every site of the dataset and append the two CSV files (reference utils/inference_utils.py:14-71).
+
+    `dl` is the dataset itself or anything with a `.dataset` attribute (a DataLoader in the reference).
+    Uses args.{out_dir, device, read_proba_threshold, num_iterations, n_processes, seed} like the reference.
+    """
+    import torch
+    ds = getattr(dl, "dataset", dl)
+    rank, world, local_rank = env_world()
+    dev = _resolve_device(args.device, local_rank, world)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=dev)
+    seed = int(getattr(args, "seed", 0))
+    n_iters = int(args.num_iterations)
+    thr = float(args.read_proba_threshold)
+    reads_per_batch = int(getattr(args, "reads_per_batch", DEFAULT_READS_PER_BATCH))
+
+    bounds = shard_bounds(ds.n_reads, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    spans = plan_batches(ds.n_reads, lo, hi, reads_per_batch)
+    n_workers = max(1, min(int(getattr(args, "n_processes", 1)), os.cpu_count() or 1))
+    sub = max(1, 256)   # sites per ingest task
+
+    site_path = os.path.join(args.out_dir, "data.site_proba.csv")
+    indiv_path = os.path.join(args.out_dir, "data.indiv_proba.csv")
+    suffix = f".rank{rank}" if world > 1 else ""
+    all_sp, all_mc = [], []
+    pool = None
+    if n_workers > 1 and len(spans):
+        # ingest workers are forked before the CUDA context exists; they only parse JSON
+        pool = ProcessPoolExecutor(n_workers, mp_context=multiprocessing.get_context("fork"), initializer=_worker_init,
+                                   initargs=(ds,))
+        list(pool.map(_worker_load, [(lo, lo)] * n_workers))
+    eng = model.engine(dev)
+    try:
+        with open(site_path + suffix, 'a', encoding='utf-8') as f, open(indiv_path + suffix, 'a', encoding='utf-8') as g:
+            for a, b in spans:
+                tasks = [(s, min(s + sub, b)) for s in range(a, b, sub)]
+                parts = list(pool.map(_worker_load, tasks)) if pool is not None else [ds.load_sites(*t) for t in tasks]
+                batch = _concat_batches(parts)
+                read_prob, site_prob, mod_count = eng.infer_host(batch.feats, batch.read_off, batch.kmer_idx, n_iters,
+                                                                 seed=seed, site_id_base=a, n_samples=N_SAMPLES,
+                                                                 read_threshold=thr)
+                write_site_rows(f, batch, site_prob, mod_count)
+                write_indiv_rows(g, batch, read_prob)
+                all_sp.append(site_prob)
+                all_mc.append(mod_count)
+    finally:
+        if pool is not None:
+            pool.shutdown()
+    site_prob = np.concatenate(all_sp) if all_sp else np.zeros(0, np.float32)
+    mod_count = np.concatenate(all_mc) if all_mc else np.zeros(0, np.int32)
+
+    if world > 1:
+        import torch.distributed as dist
+        sp_t, mc_t = all_gather_site_outputs(torch.from_numpy(site_prob).to(dev), torch.from_numpy(mod_count).to(dev), bounds)
+        site_prob, mod_count = sp_t.cpu().numpy(), mc_t.cpu().numpy()
+        dist.barrier()
+        if rank == 0:    # concatenate the shard files in site order behind the headers
+            for path in (site_path, indiv_path):
+                with open(path, 'ab') as out:
+                    for r in range(world):
+                        with open(f"{path}.rank{r}", 'rb') as part:
+                            shutil.copyfileobj(part, out)
+                        os.remove(f"{path}.rank{r}")
+        dist.barrier()
+    return site_prob, mod_count
+
+
+def main(args):
+    input_dir = args.input_dir
+    if args.model_state_dict is not None:
+        warnings.warn("--model_state_dict is specified, overwriting default model weights")
+    else:
+        if args.pretrained_model not in DEFAULT_PRETRAINED_MODELS:
+            raise ValueError("Invalid pretrained model {}, must be one of {}".format(args.pretrained_model,
+                                                                                     DEFAULT_PRETRAINED_MODELS))
+        args.model_state_dict = PRETRAINED_CONFIGS[args.pretrained_model][0]
+        args.read_proba_threshold = PRETRAINED_CONFIGS[args.pretrained_model][1]
+        args.norm_path = PRETRAINED_CONFIGS[args.pretrained_model][2]
+
+    model = MILModel(load_model_config(args.model_config)).to(args.device)
+    model.load_weights(args.model_state_dict)
+
+    rank, world, _ = env_world()
+    pathlib.Path(args.out_dir).mkdir(parents=True, exist_ok=True)
+    if rank == 0:      # headers truncate the outputs (reference scripts/inference.py:94-97)
+        with open(os.path.join(args.out_dir, "data.site_proba.csv"), 'w', encoding='utf-8') as f:
+            f.write(SITE_HEADER)
+        with open(os.path.join(args.out_dir, "data.indiv_proba.csv"), 'w', encoding='utf-8') as g:
+            g.write(INDIV_HEADER)
+    for name in ("data.site_proba.csv", "data.indiv_proba.csv"):
+        stale = os.path.join(args.out_dir, f"{name}.rank{rank}")
+        if world > 1 and os.path.exists(stale):
+            os.remove(stale)
+
+    if len(input_dir) == 1:
+        ds = NanopolishDS(input_dir[0], DEFAULT_MIN_READS, args.norm_path, mode='Inference')
+    else:
+        ds = NanopolishReplicateDS(input_dir, DEFAULT_MIN_READS, args.norm_path, mode='Inference')
+    run_inference(model, ds, args)

@@ -1,0 +1,165 @@
+"""CPU tests of the host-side mirror of the reference interface: registry, model-config plugin,
+dataset ingest (bit-exact against the reference's NanopolishDS output), CSV row formats, sharding."""
+import gzip
+import io
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from conftest import ASSETS, GOLDEN, MODEL_FILES
+
+
+@pytest.fixture(scope="session")
+def bundled_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("bundled")
+    with gzip.open(os.path.join(GOLDEN, "bundled", "data.json.gz"), "rb") as f, open(d / "data.json", "wb") as g:
+        shutil.copyfileobj(f, g)
+    shutil.copyfile(os.path.join(GOLDEN, "bundled", "data.info"), d / "data.info")
+    return str(d)
+
+
+def test_registry_mirrors_reference():
+    from m6anet_b200 import constants as C
+    assert C.DEFAULT_PRETRAINED_MODELS == ['HCT116_RNA002', 'arabidopsis_RNA002', 'HEK293T_RNA004']
+    assert set(C.PRETRAINED_CONFIGS) == set(C.DEFAULT_PRETRAINED_MODELS) | {'HEK293T_RNA004_M6ACE'}
+    assert C.PRETRAINED_CONFIGS['arabidopsis_RNA002'][1] == 0.0032978046219796
+    assert C.PRETRAINED_CONFIGS['HEK293T_RNA004'][1:] == (C.DEFAULT_READ_THRESHOLD, C.DEFAULT_NORM_PATH)
+    for w, _, n in C.PRETRAINED_CONFIGS.values():
+        assert os.path.exists(w) and os.path.exists(n)
+    assert len(C.ALL_KMERS) == 66 and list(C.ALL_KMERS) == sorted(C.ALL_KMERS) and len(C.M6A_KMERS) == 18
+    assert {C.KMER_TO_INT[k] for k in ("GGGAC", "GGACT", "GACTT")} == {45, 50, 51}
+
+
+def test_model_config_plugin_and_state_dict_keys():
+    from m6anet_b200 import constants as C
+    from m6anet_b200.model import MILModel, load_model_config
+    m = MILModel(load_model_config(C.DEFAULT_MODEL_CONFIG))
+    assert (m.n_sig, m.emb_dim, m.n_kmer, m.h1, m.h2, m.bn1, m.bn2, m.n_reads_per_site) == (9, 2, 66, 150, 32, True, False, 20)
+    keys = m.expected_keys()
+    assert keys["read_level_encoder.1.embedding_layer.weight"] == (66, 2)
+    assert keys["read_level_encoder.3.layers.1.running_var"] == (150,)
+    assert keys["read_level_encoder.4.layers.0.weight"] == (32, 150) and "read_level_encoder.4.layers.1.weight" not in keys
+    m.load_weights(C.DEFAULT_MODEL_WEIGHTS)
+    w = m.encoder_weights()
+    from m6anet_b200 import weights as W
+    w2 = W.from_npz(C.DEFAULT_MODEL_WEIGHTS)
+    for k in ("emb", "w1", "b1", "w2", "b2", "w3", "b3"):
+        assert np.array_equal(getattr(w, k), getattr(w2, k))
+    s = MILModel(load_model_config(os.path.join(ASSETS, "model_configs", "prod_pooling_signal.toml")))
+    assert (s.emb_dim, s.in1) == (0, 9) and "read_level_encoder.2.layers.0.weight" in s.expected_keys()
+    with pytest.raises(RuntimeError, match="missing keys"):
+        s.load_state_dict({})
+
+
+def test_unsupported_blocks_are_rejected_loudly():
+    from m6anet_b200.model import MILModel
+    base = [{"block_type": "DeaggregateNanopolish", "num_neighboring_features": 1}, {"block_type": "ExtractSignal"},
+            {"block_type": "Linear", "input_channel": 9, "output_channel": 150, "activation": "relu", "batch_norm": True},
+            {"block_type": "Linear", "input_channel": 150, "output_channel": 32, "activation": "relu", "batch_norm": False}]
+    with pytest.raises(NotImplementedError, match="probability_layer"):
+        MILModel({"block": base + [{"block_type": "Attention", "input_channel": 32, "hidden_layers_1": 8}]})
+    with pytest.raises(AttributeError):
+        MILModel({"block": base + [{"block_type": "NoSuchBlock"}]})
+    with pytest.raises(NotImplementedError):
+        MILModel({"block": base})
+    ok = MILModel({"block": base + [{"block_type": "SigmoidMeanPooling", "input_channel": 32}]})
+    assert ok.pooling_filter.block_type == "SigmoidMeanPooling"
+
+
+def test_dataset_matches_reference_ingest_bit_for_bit(bundled_dir, bundled_flat):
+    """features/k-mer ids/read ids equal what the reference's NanopolishDS + inference_collate produced."""
+    from m6anet_b200 import constants as C
+    from m6anet_b200.data import NanopolishDS, inference_collate
+    ds = NanopolishDS(bundled_dir, 20, C.DEFAULT_NORM_PATH, mode='Inference')
+    assert len(ds) == 101 and ds.total_neighboring_features == 1 and list(ds.indices) == list(range(9))
+    b = ds.load_sites(0, len(ds))
+    g = bundled_flat
+    assert np.array_equal(b.read_off, g["read_off"]) and np.array_equal(b.kmer_idx, g["kmer_idx"])
+    assert np.array_equal(b.feats, g["feats"])                      # float64 normalisation, one rounding: identical bits
+    assert np.array_equal(b.read_ids, g["read_id"].astype(np.int64))
+    assert np.array_equal(b.tx_ids, g["tx_id"]) and np.array_equal(b.tx_pos, g["tx_pos"])
+    assert set(b.kmers) == {"GGACT"}
+    feats, kmers, n_reads, tx, pos, rid = inference_collate([ds[0], ds[1]])
+    assert feats.shape == (662 + 441, 9) and kmers.shape == (662 + 441, 3) and list(n_reads) == [662, 441]
+    assert np.array_equal(kmers[0], g["kmer_idx"][0]) and tx[0] == "ENST00000393394.5" and pos[-1] == 234
+    # a reference .joblib-free path: norm factors load from npz with the same values
+    assert len(ds.norm_dict) == 1024 and ds.norm_dict["AAACG"][0].dtype == np.float64
+    ds.close()
+
+
+def test_replicate_dataset_pools_sites(bundled_dir, tmp_path, bundled_flat):
+    from m6anet_b200 import constants as C
+    from m6anet_b200.data import NanopolishDS, NanopolishReplicateDS
+    rep = tmp_path / "rep1"
+    shutil.copytree(bundled_dir, rep)
+    # second replicate lacks the first site and has a private one
+    lines = open(rep / "data.info").read().splitlines()
+    with open(rep / "data.info", "w") as f:
+        f.write("\n".join([lines[0]] + lines[2:]) + "\n")
+    single = NanopolishDS(bundled_dir, 20, C.DEFAULT_NORM_PATH)
+    ds = NanopolishReplicateDS([bundled_dir, str(rep)], 20, C.DEFAULT_NORM_PATH)
+    # sites with >= 20 pooled reads: all 248 keys of dir 0, pooled counts double except the first
+    import pandas as pd
+    info = pd.read_csv(os.path.join(bundled_dir, "data.info"))
+    pooled = info["n_reads"].to_numpy() * 2
+    pooled[0] = info["n_reads"][0]
+    assert len(ds) == int((pooled >= 20).sum())
+    assert ds.n_reads[0] == 662 and ds.n_reads[1] == 882
+    b = ds.load_sites(0, 2)
+    assert list(np.diff(b.read_off)) == [662, 882]
+    assert b.read_ids[0].endswith("_0") and b.read_ids[662 + 441].endswith("_1") and b.read_ids[662 + 441].split("_")[0] == b.read_ids[662].split("_")[0]
+    s1 = single.load_sites(1, 2)
+    assert np.array_equal(b.feats[662:662 + 441], s1.feats) and np.array_equal(b.feats[662 + 441:], s1.feats)
+
+
+def test_csv_row_formats_match_reference(bundled_flat):
+    """'%s,%d,%s,%.16f,%s,%.16f' and '%s,%d,%s,%.16f' (reference utils/inference_utils.py:59-67)."""
+    from m6anet_b200.data import SiteBatch
+    from m6anet_b200.inference import write_indiv_rows, write_site_rows
+    batch = SiteBatch(np.zeros((3, 9), np.float32), np.array([0, 2, 3]), np.zeros((2, 3), np.int32), np.array([966210, 7, 8]),
+                      np.array(["ENST1.5", "ENST2"]), np.array([130, 7]), np.array(["GGACT", "AAACA"]))
+    f, g = io.StringIO(), io.StringIO()
+    write_site_rows(f, batch, np.array([0.25, np.float32(0.1)], np.float32), np.array([1, 0], np.int32))
+    write_indiv_rows(g, batch, np.array([0.5, 0.125, np.float32(1e-20)], np.float32))
+    assert f.getvalue().splitlines()[0] == "ENST1.5,130,2,0.2500000000000000,GGACT,0.5000000000000000"
+    assert f.getvalue().splitlines()[1] == "ENST2,7,1,%.16f,AAACA,0.0000000000000000" % float(np.float32(0.1))
+    assert g.getvalue().splitlines() == ["ENST1.5,130,966210,0.5000000000000000", "ENST1.5,130,7,0.1250000000000000",
+                                         "ENST2,7,8,0.0000000000000000"]
+
+
+def test_argparser_keeps_reference_flags():
+    from m6anet_b200 import constants as C
+    from m6anet_b200.inference import argparser
+    a = argparser().parse_args(["--input_dir", "x", "y", "--out_dir", "o"])
+    assert a.input_dir == ["x", "y"] and a.pretrained_model == "HCT116_RNA002" and a.num_iterations == 1000
+    assert (a.batch_size, a.save_per_batch, a.n_processes, a.seed) == (16, 2, 25, 0)
+    assert a.read_proba_threshold == C.DEFAULT_READ_THRESHOLD and a.model_state_dict is None and a.device == "cuda"
+
+
+def test_main_rejects_unknown_pretrained_model_and_cpu_device(bundled_dir, tmp_path):
+    from m6anet_b200 import inference
+    a = inference.argparser().parse_args(["--input_dir", bundled_dir, "--out_dir", str(tmp_path), "--pretrained_model", "nope"])
+    with pytest.raises(ValueError, match="Invalid pretrained model"):
+        inference.main(a)
+    a = inference.argparser().parse_args(["--input_dir", bundled_dir, "--out_dir", str(tmp_path), "--device", "cpu"])
+    with pytest.raises(RuntimeError, match="no CPU"):
+        inference.main(a)
+
+
+def test_shard_bounds_balance_reads():
+    from m6anet_b200.dist import shard_bounds
+    from m6anet_b200.inference import plan_batches
+    rng = np.random.default_rng(0)
+    n = rng.integers(20, 1000, size=5000)
+    for w in (1, 2, 3, 8):
+        b = shard_bounds(n, w)
+        assert b[0] == 0 and b[-1] == 5000 and len(b) == w + 1 and all(x <= y for x, y in zip(b[:-1], b[1:]))
+        tot = [n[b[i]:b[i + 1]].sum() for i in range(w)]
+        assert max(tot) - min(tot) <= 2 * n.max()
+    assert shard_bounds(np.array([], dtype=np.int64), 4) == [0, 0, 0, 0, 0]
+    assert shard_bounds(np.full(8, 50), 8) == list(range(9))
+    spans = plan_batches(n, 100, 4000, 50_000)
+    assert spans[0][0] == 100 and spans[-1][1] == 4000 and all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+    assert all(n[a:b].sum() < 50_000 + 1000 for a, b in spans)
