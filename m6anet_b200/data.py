@@ -122,18 +122,18 @@ class NanopolishDS:
         return (len(kmer) - 5) // 2
 
     # ---- raw access ------------------------------------------------------------------------------------
-    def _handle(self, path: str):
-        f = self._files.get(path)
-        if f is None:
-            f = open(path, "rb")
-            self._files[path] = f
-        return f
+    def _handle(self, path: str) -> int:
+        fd = self._files.get(path)
+        if fd is None:
+            fd = os.open(path, os.O_RDONLY)
+            self._files[path] = fd
+        return fd
 
     def _load_data(self, data_fpath: str, tx_id: str, tx_pos: int, start_pos: int, end_pos: int):
         """One site's JSON line -> (sequence, float64 array [n, 3*(2T+1)+1]) (data_utils.py:169-190)."""
-        f = self._handle(data_fpath)
-        f.seek(start_pos, 0)
-        pos_info = json.loads(f.read(end_pos - start_pos))[tx_id][str(tx_pos)]
+        # positioned read: forked ingest workers share the descriptor, so no seek (shared file offset)
+        raw = os.pread(self._handle(data_fpath), end_pos - start_pos, start_pos)
+        pos_info = json.loads(raw)[tx_id][str(tx_pos)]
         assert len(pos_info.keys()) == 1
         kmer, features = next(iter(pos_info.items()))
         return kmer, np.array(features, dtype=np.float64)
@@ -204,8 +204,8 @@ class NanopolishDS:
             kmers=centre)
 
     def close(self):
-        for f in self._files.values():
-            f.close()
+        for fd in self._files.values():
+            os.close(fd)
         self._files = {}
 
     def __getstate__(self):   # file handles do not cross process boundaries (worker pools)
