@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libm6anet_b200.so")
+# M6A_LIB selects an alternative build of the same library (kernel A/B experiments); never a fallback.
+LIB_PATH = os.environ.get("M6A_LIB") or os.path.join(_HERE, "libm6anet_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 EXPORTS = (

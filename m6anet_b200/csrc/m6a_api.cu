@@ -136,7 +136,7 @@ extern "C" int m6a_model_destroy(m6a_model_t* model) {
 
 static int sites_per_tile_for(long long n_sites, long long total_reads) {
   const long long avg = std::max<long long>(1, (total_reads + n_sites - 1) / std::max<long long>(1, n_sites));
-  long long g = kChunkReads / avg;
+  long long g = kTileReads / avg;
   return static_cast<int>(std::min<long long>(kSitesPerTileMax, std::max<long long>(1, g)));
 }
 

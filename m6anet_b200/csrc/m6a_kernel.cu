@@ -130,7 +130,7 @@ __device__ __forceinline__ float mc_lane_generic(const float* qbase, bool from_p
 
 // -------------------------------------------------------------------------------------------------
 template <int NS>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 mil_infer_kernel(const KernelArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);

@@ -8,12 +8,33 @@
 
 namespace m6a {
 
-constexpr int kThreads = 256;
+// Tunables (overridable at build time for A/B experiments: make EXTRA="-DM6A_RPT=1 -DM6A_CTAS=3 ...")
+#ifndef M6A_THREADS
+#define M6A_THREADS 256
+#endif
+#ifndef M6A_RPT
+#define M6A_RPT 2
+#endif
+#ifndef M6A_CTAS
+#define M6A_CTAS 2
+#endif
+#ifndef M6A_GMAX
+#define M6A_GMAX 32
+#endif
+#ifndef M6A_QCAP
+#define M6A_QCAP 4096
+#endif
+#ifndef M6A_TILE_READS
+#define M6A_TILE_READS (M6A_THREADS * M6A_RPT)
+#endif
+constexpr int kThreads = M6A_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kReadsPerThread = 2;
+constexpr int kReadsPerThread = M6A_RPT;
+constexpr int kCtasPerSm = M6A_CTAS;
 constexpr int kChunkReads = kThreads * kReadsPerThread;  // feature rows staged per bulk copy
-constexpr int kSitesPerTileMax = 32;
-constexpr int kQCap = 4096;             // q = 1-p entries kept in shared memory per tile
+constexpr int kTileReads = M6A_TILE_READS;               // target reads per tile (sites_per_tile = kTileReads / mean reads)
+constexpr int kSitesPerTileMax = M6A_GMAX;
+constexpr int kQCap = M6A_QCAP;         // q = 1-p entries kept in shared memory per tile
 constexpr int kCStride = kH1Max;        // even (float2 loads); 152 mod 32 = 24 keeps neighbouring site rows on distinct banks
 constexpr int kMcMaxBlocks = 64;        // == kMaxBlocks in m6a_rng.cuh: Monte-Carlo partial sums per site
 constexpr int kMcMinItersPerLane = 8;

@@ -47,3 +47,35 @@ def main(path, top=25):
 
 if __name__ == "__main__":
     main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 25)
+
+
+def regions(path):
+    """Bucket samples into the read-encoder loop (FFMA2 range), the MC loop (MWC multiplier range) and the rest."""
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    hdr = rows[hi]
+    col = {h: i for i, h in enumerate(hdr)}
+    body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    src = [r[col["Source"]] for r in body]
+    fa = [i for i, s in enumerate(src) if "FFMA2" in s]
+    fb = [i for i, s in enumerate(src) if "147e5" in s]
+    A = (min(fa) - 12, max(fa) + 12) if fa else (0, -1)
+    B = (min(fb) - 30, max(fb) + 40) if fb else (0, -1)
+    stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    tot = sum(int(r[col["# Samples"]]) for r in body)
+    print(f"\nregions (SASS index ranges): encoder loop {A}, MC loop {B}; total samples {tot}")
+    for name, sel in (("encoder loop", lambda i: A[0] <= i <= A[1]), ("MC loop", lambda i: B[0] <= i <= B[1]),
+                      ("other", lambda i: not (A[0] <= i <= A[1]) and not (B[0] <= i <= B[1]))):
+        rs = [r for i, r in enumerate(body) if sel(i)]
+        n = sum(int(r[col["# Samples"]]) for r in rs)
+        inst = sum(int(r[col["Instructions Executed"]]) for r in rs)
+        st = Counter()
+        for r in rs:
+            for h in stall_cols:
+                st[h] += int(r[col[h]] or 0)
+        top = ", ".join(f"{h[6:]} {100*v/max(1,n):.0f}%" for h, v in st.most_common(6))
+        print(f"  {name:13s} samples {100*n/max(1,tot):5.1f}%  warp-instr {inst:15,d}   {top}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1:
+    regions(sys.argv[1])
