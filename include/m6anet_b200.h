@@ -17,6 +17,10 @@
  *                              calculate_site_proba/_calculate_site_proba   (:54,74-104)
  *   m6a_mil_infer_host_f32  the same, including features.to(device) / probs.cpu()  (:35-36,41)
  *   m6a_sample_indices      np.random.choice index draw                     (:85)
+ *   m6a_ingest_parts        NanopolishDS._load_data/__getitem__/get_norm_factor + inference_collate,
+ *                            NanopolishReplicateDS.load_data                 utils/data_utils.py:152-248,395-427,498-506
+ *   m6a_write_site_csv      the site rows   '%s,%d,%s,%.16f,%s,%.16f'       utils/inference_utils.py:59-60
+ *   m6a_write_indiv_csv     the read rows   '%s,%d,%s,%.16f'                utils/inference_utils.py:63-64
  *
  * Conventions: plain C types only; no exceptions cross the boundary; every function returns an
  * int status (0 = ok, <0 = M6A_E*, >0 = a cudaError_t value) readable with m6a_strerror().
@@ -40,6 +44,8 @@ extern "C" {
 #define M6A_EALIGN (-3)       /* a device buffer is not aligned as documented                */
 #define M6A_ERANGE (-4)       /* a site has more reads than the mode allows                  */
 #define M6A_ENOMEM (-5)       /* host allocation failed                                      */
+#define M6A_EPARSE (-6)       /* a data.json site line does not match data.info / the format  */
+#define M6A_EIO (-7)          /* open/read/write failed                                      */
 
 /* Compiled limits of the kernel (see m6anet_b200/csrc/m6a_layout.h). */
 #define M6A_N_SIG 9          /* signal features per read: 3 positions x (dwell, sd, mean)   */
@@ -122,6 +128,46 @@ int m6a_mil_infer_host_f32(const m6a_model_t *model, const float *feats, const i
  * Test hook proving the device generator equals oracle/philox.py bit for bit. */
 int m6a_sample_indices(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters,
                        int32_t n_samples, int32_t *out, void *stream);
+
+/*
+ * ---- host I/O of the path (multi-threaded, no CUDA) ------------------------------------------------
+ * One part = one site line of one data.json file: `{"<tx>":{"<pos>":{"<7-mer>":[[f0..f8, read_id], ...]}}}`
+ * in the byte range [start, end) (data.info columns start/end; reference utils/dataprep_utils.py:473-485).
+ * A site has one part per input directory that contains it (replicates are concatenated in part order).
+ */
+typedef struct {
+  int32_t file;          /* index into paths[]                                              */
+  int32_t rep;           /* replicate number (informational)                                */
+  int64_t start, end;    /* byte range of the line                                          */
+  int64_t row_off;       /* first output row of this part                                   */
+  int64_t n_rows;        /* rows expected (data.info n_reads); a mismatch is M6A_EPARSE      */
+  int64_t site;          /* output site index (row of kmer_idx)                             */
+  int32_t first_of_site; /* 1: this part writes kmer_idx[site]                              */
+  int32_t reserved;
+} m6a_part_t;
+
+/*
+ * Parses the parts with n_threads workers (0 = all cores) into
+ *   feats    [rows, 3*(2*n_flank+1)] float32 = (raw - mean) / std evaluated in float64, rounded once
+ *   read_ids [rows] int64, kmer_idx [n_sites, 2*n_flank+1] int32
+ * norm_mean / norm_std: [1024, 3] float64 indexed by the base-4 code of a five-mer (A,C,G,T = 0..3,
+ * first letter most significant), NaN = five-mer absent from the norm factors; kmer_id: [1024] five-mer
+ * code -> id of the 66-entry table (-1 = none).  *bad_part receives the index of the first failing part.
+ */
+int m6a_ingest_parts(const char *const *paths, int32_t n_files, const m6a_part_t *parts, int64_t n_parts,
+                     int32_t n_flank, const double *norm_mean, const double *norm_std,
+                     const int32_t *kmer_id, float *feats, int64_t *read_ids, int32_t *kmer_idx,
+                     int32_t n_threads, int64_t *bad_part);
+
+/* Appends the reference-format rows to the open file descriptor fd (rows are formatted by n_threads
+ * workers and written in site order).  tx_buf/tx_off: concatenated transcript ids, CSR offsets [n_sites+1];
+ * kmer5: [n_sites, 5] chars (centre five-mer); read_rep NULL => integer read_index, else "{id}_{rep}". */
+int m6a_write_site_csv(int32_t fd, int64_t n_sites, const char *tx_buf, const int64_t *tx_off,
+                       const int64_t *tx_pos, const int64_t *read_off, const float *site_prob,
+                       const int32_t *mod_count, const char *kmer5, int32_t n_threads);
+int m6a_write_indiv_csv(int32_t fd, int64_t n_sites, const char *tx_buf, const int64_t *tx_off,
+                        const int64_t *tx_pos, const int64_t *read_off, const int64_t *read_ids,
+                        const int32_t *read_rep, const float *read_prob, int32_t n_threads);
 
 /* Launch geometry of the last m6a_mil_infer_f32 call on this thread (for bench/roofline
  * reporting): grid, block, dynamic smem bytes, sites per tile, number of kernel launches. */

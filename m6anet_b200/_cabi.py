@@ -16,8 +16,15 @@ CSRC = os.path.join(_HERE, "csrc")
 
 EXPORTS = (
     "m6a_version", "m6a_strerror", "m6a_model_create", "m6a_model_destroy", "m6a_mil_infer_f32",
-    "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_last_launch",
+    "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_last_launch", "m6a_ingest_parts", "m6a_write_site_csv",
+    "m6a_write_indiv_csv",
 )
+
+# struct m6a_part_t as a NumPy record (56 bytes, natural alignment)
+import numpy as _np
+PART_DTYPE = _np.dtype([("file", "<i4"), ("rep", "<i4"), ("start", "<i8"), ("end", "<i8"), ("row_off", "<i8"),
+                        ("n_rows", "<i8"), ("site", "<i8"), ("first_of_site", "<i4"), ("reserved", "<i4")], align=True)
+assert PART_DTYPE.itemsize == 56
 
 
 class M6AWeights(C.Structure):
@@ -76,6 +83,12 @@ def lib() -> C.CDLL:
     L.m6a_sample_indices.argtypes = [u64, i64, i32, i32, i32, vp, vp]
     L.m6a_last_launch.restype = C.c_int
     L.m6a_last_launch.argtypes = [C.POINTER(i32)] * 5
+    L.m6a_ingest_parts.restype = C.c_int
+    L.m6a_ingest_parts.argtypes = [C.POINTER(C.c_char_p), i32, vp, i64, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(i64)]
+    L.m6a_write_site_csv.restype = C.c_int
+    L.m6a_write_site_csv.argtypes = [i32, i64, vp, vp, vp, vp, vp, vp, vp, i32]
+    L.m6a_write_indiv_csv.restype = C.c_int
+    L.m6a_write_indiv_csv.argtypes = [i32, i64, vp, vp, vp, vp, vp, vp, vp, i32]
     _lib = L
     return L
 

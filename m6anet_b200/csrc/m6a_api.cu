@@ -46,6 +46,8 @@ extern "C" const char* m6a_strerror(int status) {
     case M6A_EALIGN: return "buffer alignment";
     case M6A_ERANGE: return "value out of range for this mode";
     case M6A_ENOMEM: return "host allocation failed";
+    case M6A_EPARSE: return "data.json site line does not match data.info or the expected format";
+    case M6A_EIO: return "file open/read/write failed";
     default: break;
   }
   if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));

@@ -1,0 +1,293 @@
+// Host-side I/O of the inference path, multi-threaded, behind the C ABI (include/m6anet_b200.h):
+//   m6a_ingest_parts    data.json byte ranges -> flat normalised float32 buffers
+//                       (reference utils/data_utils.py:152-248 _load_data/load_data/__getitem__/get_norm_factor,
+//                        :395-427 replicate concatenation; file format utils/dataprep_utils.py:473-485)
+//   m6a_write_site_csv / m6a_write_indiv_csv   the reference row formats (utils/inference_utils.py:59-67)
+// Numbers are parsed with std::from_chars (correctly rounded, == Python float()), normalised in double and
+// rounded once to float32, so the buffers equal the reference's NanopolishDS output bit for bit.
+#include <fcntl.h>
+#include <stdio.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/m6anet_b200.h"
+
+namespace {
+
+inline int base_code(char c) {
+  switch (c) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': return 3;
+    default: return -1;
+  }
+}
+
+// 5-mer at s -> base-4 code in [0, 1024), -1 if a letter is not ACGT
+inline int kmer5_code(const char* s) {
+  int code = 0;
+  for (int i = 0; i < 5; ++i) {
+    const int b = base_code(s[i]);
+    if (b < 0) return -1;
+    code = code * 4 + b;
+  }
+  return code;
+}
+
+struct IngestCtx {
+  const char* const* paths;
+  const m6a_part_t* parts;
+  int64_t n_parts;
+  int n_flank;
+  const double* norm_mean;
+  const double* norm_std;
+  const int32_t* kmer_id;
+  float* feats;
+  int64_t* read_ids;
+  int32_t* kmer_idx;
+  std::vector<int> fds;
+  std::atomic<int64_t> next{0};
+  std::atomic<int64_t> bad{-1};
+  std::atomic<int> status{M6A_OK};
+};
+
+void fail(IngestCtx& c, int64_t part, int status) {
+  int expected = M6A_OK;
+  if (c.status.compare_exchange_strong(expected, status)) c.bad.store(part);
+}
+
+// Parse one site line: {"tx":{"pos":{"KMER":[[v,...,v],[...]]}}}
+bool parse_part(IngestCtx& c, int64_t pi, std::vector<char>& buf) {
+  const m6a_part_t& p = c.parts[pi];
+  const int64_t len = p.end - p.start;
+  if (len <= 0 || p.file < 0) return false;
+  buf.resize(static_cast<size_t>(len) + 1);
+  int64_t got = 0;
+  while (got < len) {
+    const ssize_t r = pread(c.fds[p.file], buf.data() + got, static_cast<size_t>(len - got), p.start + got);
+    if (r <= 0) {
+      fail(c, pi, M6A_EIO);
+      return true;  // status already set
+    }
+    got += r;
+  }
+  buf[len] = 0;
+  const char* s = buf.data();
+  const char* e = s + len;
+  // the third '{' opens {"KMER":[[...
+  int braces = 0;
+  const char* q = s;
+  for (; q < e; ++q) {
+    if (*q == '"') {  // skip strings
+      for (++q; q < e && *q != '"'; ++q) {}
+      continue;
+    }
+    if (*q == '{' && ++braces == 3) break;
+  }
+  if (q >= e) return false;
+  const char* k0 = static_cast<const char*>(memchr(q, '"', e - q));
+  if (!k0) return false;
+  ++k0;
+  const char* k1 = static_cast<const char*>(memchr(k0, '"', e - k0));
+  if (!k1) return false;
+  const int klen = static_cast<int>(k1 - k0);
+  if (klen < 5 || ((klen - 5) & 1)) return false;
+  const int T = (klen - 5) / 2, n = c.n_flank;       // flanks in the file / wanted
+  if (n > T) return false;
+  const int n_pos = 2 * n + 1, n_sig = 3 * n_pos, row_w = 3 * (2 * T + 1) + 1;
+  // five-mers of the centred (5+2n)-mer, normalisation vectors, ids
+  double mean[33], stdv[33];
+  int32_t ids[11];
+  for (int j = 0; j < n_pos; ++j) {
+    const int code = kmer5_code(k0 + (T - n) + j);
+    if (code < 0 || c.kmer_id[code] < 0) return false;
+    ids[j] = c.kmer_id[code];
+    for (int i = 0; i < 3; ++i) {
+      mean[3 * j + i] = c.norm_mean[3 * code + i];
+      stdv[3 * j + i] = c.norm_std[3 * code + i];
+      if (std::isnan(mean[3 * j + i]) || std::isnan(stdv[3 * j + i])) return false;   // k-mer missing from norm factors
+    }
+  }
+  int32_t* kid = c.kmer_idx + p.site * n_pos;
+  if (p.first_of_site) {
+    for (int j = 0; j < n_pos; ++j) kid[j] = ids[j];
+  }
+  const int col0 = (T - n) * 3;   // selected signal columns are contiguous: [(T-n)*3, (T+n+1)*3)
+  // rows
+  const char* r = k1 + 1;
+  double vals[40];
+  int64_t row = 0;
+  while (r < e) {
+    // find next '[' that starts a row (skip the outer one)
+    while (r < e && *r != '[' && *r != '}') ++r;
+    if (r >= e || *r == '}') break;
+    ++r;
+    if (r < e && *r == '[') continue;   // outer bracket: next loop iteration finds the inner one
+    if (r < e && *r == ']') break;      // empty list
+    int nv = 0;
+    while (r < e) {
+      while (r < e && (*r == ' ' || *r == ',')) ++r;
+      if (r < e && *r == ']') { ++r; break; }
+      if (nv >= 40) return false;
+      double v;
+      auto res = std::from_chars(r, e, v);
+      if (res.ec != std::errc()) {
+        if (e - r >= 3 && !strncmp(r, "NaN", 3)) { v = NAN; res.ptr = r + 3; }
+        else return false;
+      }
+      vals[nv++] = v;
+      r = res.ptr;
+    }
+    if (nv != row_w) return false;
+    if (row >= p.n_rows) return false;
+    float* out = c.feats + (p.row_off + row) * n_sig;
+    for (int k = 0; k < n_sig; ++k) out[k] = static_cast<float>((vals[col0 + k] - mean[k]) / stdv[k]);
+    c.read_ids[p.row_off + row] = static_cast<int64_t>(vals[row_w - 1]);
+    ++row;
+  }
+  return row == p.n_rows;
+}
+
+void ingest_worker(IngestCtx* c) {
+  std::vector<char> buf;
+  for (;;) {
+    const int64_t i = c->next.fetch_add(1);
+    if (i >= c->n_parts || c->status.load() != M6A_OK) return;
+    if (!parse_part(*c, i, buf)) fail(*c, i, M6A_EPARSE);
+  }
+}
+
+int n_workers(int32_t n_threads, int64_t items) {
+  int n = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
+  if (n < 1) n = 1;
+  if (n > 256) n = 256;
+  if (static_cast<int64_t>(n) > items) n = static_cast<int>(items > 0 ? items : 1);
+  return n;
+}
+
+bool write_all(int fd, const char* p, size_t n) {
+  while (n > 0) {
+    const ssize_t w = write(fd, p, n);
+    if (w <= 0) return false;
+    p += w;
+    n -= static_cast<size_t>(w);
+  }
+  return true;
+}
+
+template <class F>
+int format_parallel(int fd, int64_t n_sites, int32_t n_threads, F&& format_range) {
+  const int nw = n_workers(n_threads, n_sites);
+  std::vector<std::string> out(nw);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nw; ++t) {
+    const int64_t a = n_sites * t / nw, b = n_sites * (t + 1) / nw;
+    th.emplace_back([&, t, a, b] { format_range(a, b, out[t]); });
+  }
+  for (auto& x : th) x.join();
+  for (int t = 0; t < nw; ++t)
+    if (!write_all(fd, out[t].data(), out[t].size())) return M6A_EIO;
+  return M6A_OK;
+}
+
+}  // namespace
+
+extern "C" int m6a_ingest_parts(const char* const* paths, int32_t n_files, const m6a_part_t* parts, int64_t n_parts,
+                                int32_t n_flank, const double* norm_mean, const double* norm_std, const int32_t* kmer_id,
+                                float* feats, int64_t* read_ids, int32_t* kmer_idx, int32_t n_threads, int64_t* bad_part) {
+  if (bad_part) *bad_part = -1;
+  if (n_parts < 0 || n_files < 0 || n_flank < 0 || n_flank > 5) return M6A_EINVAL;
+  if (n_parts == 0) return M6A_OK;
+  if (!paths || !parts || !norm_mean || !norm_std || !kmer_id || !feats || !read_ids || !kmer_idx) return M6A_EINVAL;
+  IngestCtx c;
+  c.paths = paths;
+  c.parts = parts;
+  c.n_parts = n_parts;
+  c.n_flank = n_flank;
+  c.norm_mean = norm_mean;
+  c.norm_std = norm_std;
+  c.kmer_id = kmer_id;
+  c.feats = feats;
+  c.read_ids = read_ids;
+  c.kmer_idx = kmer_idx;
+  for (int f = 0; f < n_files; ++f) {
+    const int fd = open(paths[f], O_RDONLY);
+    if (fd < 0) {
+      for (int g : c.fds) close(g);
+      return M6A_EIO;
+    }
+    c.fds.push_back(fd);
+  }
+  for (int64_t i = 0; i < n_parts; ++i)
+    if (parts[i].file >= n_files) {
+      for (int g : c.fds) close(g);
+      return M6A_EINVAL;
+    }
+  const int nw = n_workers(n_threads, n_parts);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nw; ++t) th.emplace_back(ingest_worker, &c);
+  for (auto& x : th) x.join();
+  for (int g : c.fds) close(g);
+  if (bad_part) *bad_part = c.bad.load();
+  return c.status.load();
+}
+
+// '%s,%d,%s,%.16f,%s,%.16f\n' % (tx_id, tx_pos, n_read, site_prob, kmer, mod_ratio)   utils/inference_utils.py:59-60
+extern "C" int m6a_write_site_csv(int32_t fd, int64_t n_sites, const char* tx_buf, const int64_t* tx_off,
+                                  const int64_t* tx_pos, const int64_t* read_off, const float* site_prob,
+                                  const int32_t* mod_count, const char* kmer5, int32_t n_threads) {
+  if (n_sites < 0) return M6A_EINVAL;
+  if (n_sites == 0) return M6A_OK;
+  if (!tx_buf || !tx_off || !tx_pos || !read_off || !site_prob || !mod_count || !kmer5) return M6A_EINVAL;
+  return format_parallel(fd, n_sites, n_threads, [&](int64_t a, int64_t b, std::string& out) {
+    char line[160];
+    out.reserve(static_cast<size_t>(b - a) * 96);
+    for (int64_t s = a; s < b; ++s) {
+      const int64_t n = read_off[s + 1] - read_off[s];
+      const double ratio = static_cast<double>(mod_count[s]) / static_cast<double>(n > 0 ? n : 1);
+      out.append(tx_buf + tx_off[s], static_cast<size_t>(tx_off[s + 1] - tx_off[s]));
+      const int m = snprintf(line, sizeof line, ",%lld,%lld,%.16f,%.5s,%.16f\n", static_cast<long long>(tx_pos[s]),
+                             static_cast<long long>(n), static_cast<double>(site_prob[s]), kmer5 + 5 * s, ratio);
+      out.append(line, static_cast<size_t>(m));
+    }
+  });
+}
+
+// '%s,%d,%s,%.16f\n' % (tx_id, tx_pos, read_id, read_prob)   utils/inference_utils.py:63-64
+// read_rep == NULL: read_index is the integer id; else "{id}_{rep}" (utils/data_utils.py:421-423)
+extern "C" int m6a_write_indiv_csv(int32_t fd, int64_t n_sites, const char* tx_buf, const int64_t* tx_off,
+                                   const int64_t* tx_pos, const int64_t* read_off, const int64_t* read_ids,
+                                   const int32_t* read_rep, const float* read_prob, int32_t n_threads) {
+  if (n_sites < 0) return M6A_EINVAL;
+  if (n_sites == 0) return M6A_OK;
+  if (!tx_buf || !tx_off || !tx_pos || !read_off || !read_ids || !read_prob) return M6A_EINVAL;
+  return format_parallel(fd, n_sites, n_threads, [&](int64_t a, int64_t b, std::string& out) {
+    char line[128];
+    out.reserve(static_cast<size_t>(read_off[b] - read_off[a]) * 64);
+    for (int64_t s = a; s < b; ++s) {
+      const char* tx = tx_buf + tx_off[s];
+      const size_t tl = static_cast<size_t>(tx_off[s + 1] - tx_off[s]);
+      char pos[32];
+      const int pl = snprintf(pos, sizeof pos, ",%lld,", static_cast<long long>(tx_pos[s]));
+      for (int64_t r = read_off[s]; r < read_off[s + 1]; ++r) {
+        out.append(tx, tl);
+        out.append(pos, static_cast<size_t>(pl));
+        int m;
+        if (read_rep)
+          m = snprintf(line, sizeof line, "%lld_%d,%.16f\n", static_cast<long long>(read_ids[r]), read_rep[r],
+                       static_cast<double>(read_prob[r]));
+        else
+          m = snprintf(line, sizeof line, "%lld,%.16f\n", static_cast<long long>(read_ids[r]), static_cast<double>(read_prob[r]));
+        out.append(line, static_cast<size_t>(m));
+      }
+    }
+  });
+}

@@ -11,8 +11,11 @@ Input format (reference utils/dataprep_utils.py:473-485): data.info is a csv
 `transcript_id,transcript_position,start,end,n_reads`; data.json holds one line per site
 `{"<tx>":{"<pos>":{"<7-mer>":[[f0..f8, read_id], ...]}}}` addressed by the `[start, end)` byte range.
 
-Besides the reference's per-site `__getitem__`, the datasets expose `load_sites(lo, hi)`, which returns
-the flat buffers the C ABI consumes (feats [R,9] f32, read_off [S+1] i64, kmer_idx [S,3] i32).
+Besides the reference's per-site `__getitem__` (Python json, reference-shaped), the datasets expose
+`load_sites(lo, hi)`, which returns the flat buffers the C ABI consumes (feats [R,9] f32, read_off [S+1] i64,
+kmer_idx [S,3] i32).  `load_sites` runs the multi-threaded native parser `m6a_ingest_parts`
+(m6anet_b200/csrc/m6a_io.cpp); tests/test_host.py checks it bit for bit against the per-site Python path and
+against the reference's own NanopolishDS output.
 Training modes and on-the-fly norm-factor computation are outside the inference path and not provided.
 """
 from __future__ import annotations
@@ -33,10 +36,11 @@ class SiteBatch:
     feats: np.ndarray        # [R, 9] float32, normalised
     read_off: np.ndarray     # [S+1] int64
     kmer_idx: np.ndarray     # [S, 3] int32
-    read_ids: np.ndarray     # [R] int64 (single dir) or object/str "{id}_{rep}" (replicates)
+    read_ids: np.ndarray     # [R] int64
     tx_ids: np.ndarray       # [S] str
     tx_pos: np.ndarray       # [S] int64
     kmers: np.ndarray        # [S] centre 5-mer (str)
+    read_rep: Optional[np.ndarray] = None   # [R] int32 replicate number (multi-directory input) -> "{id}_{rep}"
 
     @property
     def n_sites(self) -> int:
@@ -93,10 +97,16 @@ class NanopolishDS:
         self._tx = self.data_info["transcript_id"].to_numpy().astype(str)
         self._pos = self.data_info["transcript_position"].to_numpy(dtype=np.int64)
         self._n_reads = self.data_info["n_reads"].to_numpy(dtype=np.int64)
-        # per site: list of (file path, start, end, replicate number)
-        start = self.data_info["start"].to_numpy(dtype=np.int64)
-        end = self.data_info["end"].to_numpy(dtype=np.int64)
-        self._parts = [[(self.data_fpath, int(s), int(e), 0)] for s, e in zip(start, end)]
+        # part tables (one part per site here): CSR pointer over sites + per-part file / byte range / replicate / rows
+        S = len(self._tx)
+        self._paths = [self.data_fpath]
+        self._part_ptr = np.arange(S + 1, dtype=np.int64)
+        self._part_file = np.zeros(S, dtype=np.int32)
+        self._part_rep = np.zeros(S, dtype=np.int32)
+        self._part_start = self.data_info["start"].to_numpy(dtype=np.int64)
+        self._part_end = self.data_info["end"].to_numpy(dtype=np.int64)
+        self._part_rows = self._n_reads.copy()
+        self._multi = False
 
     def __len__(self) -> int:
         return len(self._tx)
@@ -117,9 +127,14 @@ class NanopolishDS:
     def get_total_neighboring_features(self) -> int:
         if len(self) == 0:
             return self.num_neighboring_features
-        path, s, e, _ = self._parts[0][0]
+        path, s, e, _ = self._site_parts(0)[0]
         kmer, _ = self._load_data(path, self._tx[0], int(self._pos[0]), s, e)
         return (len(kmer) - 5) // 2
+
+    def _site_parts(self, idx: int):
+        a, b = int(self._part_ptr[idx]), int(self._part_ptr[idx + 1])
+        return [(self._paths[self._part_file[i]], int(self._part_start[i]), int(self._part_end[i]), int(self._part_rep[i]))
+                for i in range(a, b)]
 
     # ---- raw access ------------------------------------------------------------------------------------
     def _handle(self, path: str) -> int:
@@ -144,7 +159,7 @@ class NanopolishDS:
     def load_data(self, idx: int):
         """(tx_id, tx_pos, read_ids, raw selected features float64 [n, 9], sequence)."""
         feats, ids, seq = [], [], None
-        for path, s, e, rep in self._parts[idx]:
+        for path, s, e, rep in self._site_parts(idx):
             kmer, arr = self._load_data(path, self._tx[idx], int(self._pos[idx]), s, e)
             if seq is None:
                 seq = kmer
@@ -183,25 +198,70 @@ class NanopolishDS:
         n = len(feats)
         return feats, np.repeat(kid[None, :], n, axis=0), np.repeat(tx_id, n), np.repeat(tx_pos, n), read_ids
 
-    # ---- flat access ------------------------------------------------------------------------------------
-    def load_sites(self, lo: int, hi: int) -> SiteBatch:
+    # ---- flat access (native parser) -----------------------------------------------------------------------
+    def _native_tables(self):
+        t = getattr(self, "_tables", None)
+        if t is None:
+            code = {"A": 0, "C": 1, "G": 2, "T": 3}
+            enc = lambda k: sum(code[ch] * 4 ** (4 - i) for i, ch in enumerate(k))
+            mean = np.full((1024, 3), np.nan)
+            std = np.full((1024, 3), np.nan)
+            for k, (m, sd) in self.norm_dict.items():
+                if len(k) == 5 and set(k) <= set("ACGT"):
+                    mean[enc(k)], std[enc(k)] = m, sd
+            kid = np.full(1024, -1, dtype=np.int32)
+            for k, i in self.kmer_to_int.items():
+                kid[enc(k)] = i
+            t = self._tables = (np.ascontiguousarray(mean), np.ascontiguousarray(std), kid)
+        return t
+
+    def load_sites(self, lo: int, hi: int, n_threads: int = 0) -> SiteBatch:
+        import ctypes as C
+        from . import _cabi
         hi = min(hi, len(self))
-        feats, ids, kids, n_reads = [], [], [], []
-        for idx in range(lo, hi):
-            _, _, read_ids, f, kid = self._site(idx)
-            feats.append(f)
-            ids.append(read_ids)
-            kids.append(kid)
-            n_reads.append(len(f))
-        S = hi - lo
+        S = max(hi - lo, 0)
+        n_pos = 2 * self.num_neighboring_features + 1
+        a, b = int(self._part_ptr[lo]), int(self._part_ptr[lo + S])
+        rows = self._part_rows[a:b]
+        parts = np.zeros(b - a, dtype=_cabi.PART_DTYPE)
+        parts["file"] = self._part_file[a:b]
+        parts["rep"] = self._part_rep[a:b]
+        parts["start"] = self._part_start[a:b]
+        parts["end"] = self._part_end[a:b]
+        parts["n_rows"] = rows
+        row_off = np.zeros(b - a + 1, dtype=np.int64)
+        np.cumsum(rows, out=row_off[1:])
+        parts["row_off"] = row_off[:-1]
+        counts = np.diff(self._part_ptr[lo:lo + S + 1])
+        parts["site"] = np.repeat(np.arange(S, dtype=np.int64), counts)
+        first = np.zeros(b - a, dtype=np.int32)
+        first[(self._part_ptr[lo:lo + S] - a)[counts > 0]] = 1
+        parts["first_of_site"] = first
+        R = int(row_off[-1])
+        feats = np.empty((R, 3 * n_pos), dtype=np.float32)
+        read_ids = np.empty(R, dtype=np.int64)
+        kmer_idx = np.zeros((S, n_pos), dtype=np.int32)
+        mean, std, kid = self._native_tables()
+        paths = (C.c_char_p * len(self._paths))(*[os.fsencode(p) for p in self._paths])
+        bad = C.c_int64(-1)
+        vp = lambda arr: arr.ctypes.data_as(C.c_void_p)
+        rc = _cabi.lib().m6a_ingest_parts(paths, len(self._paths), vp(parts), len(parts), self.num_neighboring_features,
+                                          vp(mean), vp(std), vp(kid), vp(feats), vp(read_ids), vp(kmer_idx), n_threads,
+                                          C.byref(bad))
+        if rc != 0:
+            where = ""
+            if bad.value >= 0:
+                i = a + bad.value
+                site = lo + int(parts["site"][bad.value])
+                where = (f" (site {self._tx[site]}:{self._pos[site]}, file {self._paths[self._part_file[i]]}, bytes "
+                         f"[{self._part_start[i]}, {self._part_end[i]}))")
+            raise _cabi.M6AError(rc, "m6a_ingest_parts" + where)
         read_off = np.zeros(S + 1, dtype=np.int64)
-        np.cumsum(n_reads, out=read_off[1:])
-        kid = np.array(kids, dtype=np.int32).reshape(S, 3) if S else np.zeros((0, 3), np.int32)
-        centre = np.array([self.int_to_kmer[int(k)] for k in kid[:, kid.shape[1] // 2]]) if S else np.array([], dtype=str)
-        return SiteBatch(
-            feats=np.concatenate(feats) if feats else np.zeros((0, 9), np.float32), read_off=read_off, kmer_idx=kid,
-            read_ids=np.concatenate(ids) if ids else np.zeros(0, np.int64), tx_ids=self._tx[lo:hi], tx_pos=self._pos[lo:hi],
-            kmers=centre)
+        read_off[1:] = row_off[1:][np.cumsum(counts) - 1] if S and (b - a) else 0
+        centre = np.array([self.int_to_kmer[int(k)] for k in kmer_idx[:, n_pos // 2]]) if S else np.array([], dtype=str)
+        rep = np.repeat(self._part_rep[a:b], rows).astype(np.int32) if self._multi else None
+        return SiteBatch(feats=feats, read_off=read_off, kmer_idx=kmer_idx, read_ids=read_ids, tx_ids=self._tx[lo:hi],
+                         tx_pos=self._pos[lo:hi], kmers=centre, read_rep=rep)
 
     def close(self):
         for fd in self._files.values():
@@ -241,17 +301,24 @@ class NanopolishReplicateDS(NanopolishDS):
         self._tx = site_key["transcript_id"].to_numpy().astype(str)[keep]
         self._pos = site_key["transcript_position"].to_numpy(dtype=np.int64)[keep]
         self._n_reads = total[keep].astype(np.int64)
-        parts: List[list] = [[] for _ in range(int(keep.sum()))]
         rows = allrows[keep[allrows["site"].to_numpy()]].sort_values(["site", "rep"], kind="stable")
-        for site, rep, s, e in zip(rows["site"].to_numpy(), rows["rep"].to_numpy(), rows["start"].to_numpy(), rows["end"].to_numpy()):
-            parts[new_id[site]].append((os.path.join(self.root_dir[rep], "data.json"), int(s), int(e), int(rep)))
-        self._parts = parts
+        site_new = new_id[rows["site"].to_numpy()]
+        self._paths = [os.path.join(d, "data.json") for d in self.root_dir]
+        self._part_file = rows["rep"].to_numpy(dtype=np.int32)
+        self._part_rep = rows["rep"].to_numpy(dtype=np.int32)
+        self._part_start = rows["start"].to_numpy(dtype=np.int64)
+        self._part_end = rows["end"].to_numpy(dtype=np.int64)
+        self._part_rows = rows["n_reads"].to_numpy(dtype=np.int64)
+        self._part_ptr = np.zeros(int(keep.sum()) + 1, dtype=np.int64)
+        np.cumsum(np.bincount(site_new, minlength=int(keep.sum())), out=self._part_ptr[1:])
+        self._multi = True
         self.data_info = pd.DataFrame({"transcript_id": self._tx, "transcript_position": self._pos, "n_reads": self._n_reads})
         self.fpath_mapping = {d: rep for rep, d in enumerate(self.root_dir)}
         self.data_fpath = None
 
     def _read_id_array(self, raw: np.ndarray, rep: int):
-        return np.array([f"{int(r)}_{rep}" for r in raw], dtype=object)                  # data_utils.py:421-423
+        """reference-shaped ids of __getitem__: "{read_id}_{replicate}" (data_utils.py:421-423)"""
+        return np.array([f"{int(r)}_{rep}" for r in raw], dtype=object)
 
 
 def inference_collate(batch):

@@ -18,13 +18,11 @@ shard, one all-gather collects the per-site outputs and the shard files are conc
 """
 from __future__ import annotations
 
-import multiprocessing
 import os
 import pathlib
 import shutil
 import warnings
 from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
-from concurrent.futures import ProcessPoolExecutor
 from typing import List, Optional
 
 import numpy as np
@@ -57,7 +55,8 @@ def argparser():
                         'compatibility, the kernel batches by --reads_per_batch).', default=16, type=int)
     parser.add_argument("--save_per_batch", help='saving inference results every save_per_batch multiples '
                         '(kept for compatibility; every site is always written).', default=2, type=int)
-    parser.add_argument("--n_processes", help='number of processes to run (JSON ingest workers).', default=25, type=int)
+    parser.add_argument("--n_processes", help='number of processes to run (here: ingest / CSV worker threads).', default=25,
+                        type=int)
     parser.add_argument("--num_iterations", help='number of sampling run.', default=1000, type=int)
     parser.add_argument("--device", help='device to perform inference with (cuda or cuda:N).', default='cuda', type=str)
     parser.add_argument("--seed", help='random seed for sampling.', default=0, type=int)
@@ -70,49 +69,47 @@ def argparser():
     return parser
 
 
-# ---- CSV emit ------------------------------------------------------------------------------------------
-def write_site_rows(f, batch: SiteBatch, site_prob: np.ndarray, mod_count: np.ndarray):
-    n_reads = np.diff(batch.read_off)
-    mod_ratio = mod_count.astype(np.float64) / np.maximum(n_reads, 1)      # np.mean(x >= thr) in float64 (:53)
-    out = []
-    for tx, pos, n, sp, kmer, mr in zip(batch.tx_ids, batch.tx_pos, n_reads, site_prob.astype(np.float64), batch.kmers, mod_ratio):
-        out.append('%s,%d,%s,%.16f,%s,%.16f\n' % (tx, pos, n, sp, kmer, mr))
-    f.write("".join(out))
+# ---- CSV emit (native, multi-threaded: m6a_write_site_csv / m6a_write_indiv_csv) -------------------------
+def _tx_buffer(tx_ids: np.ndarray):
+    enc = [str(t).encode("utf-8") for t in tx_ids]
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in enc], out=off[1:])
+    return b"".join(enc), off
 
 
-def write_indiv_rows(g, batch: SiteBatch, read_prob: np.ndarray):
-    n_reads = np.diff(batch.read_off)
-    tx = np.repeat(batch.tx_ids, n_reads)
-    pos = np.repeat(batch.tx_pos, n_reads)
-    out = []
-    for t, p, rid, rp in zip(tx, pos, batch.read_ids, read_prob.astype(np.float64)):
-        out.append('%s,%d,%s,%.16f\n' % (t, p, rid, rp))
-    g.write("".join(out))
+def _vp(a):
+    import ctypes as C
+    return a.ctypes.data_as(C.c_void_p)
 
 
-# ---- ingest helpers ----------------------------------------------------------------------------------------
-_WORKER_DS = None
+def write_site_rows(f, batch: SiteBatch, site_prob: np.ndarray, mod_count: np.ndarray, n_threads: int = 0):
+    """'%s,%d,%s,%.16f,%s,%.16f' rows (tx_id, tx_pos, n_reads, site_prob, kmer, mod_ratio) appended to file object f;
+    mod_ratio = mod_count / n_reads in float64 == np.mean(p >= thr) (reference utils/inference_utils.py:53,59-60)."""
+    from . import _cabi
+    f.flush()
+    tx, off = _tx_buffer(batch.tx_ids)
+    kmer5 = "".join(str(k)[:5].ljust(5) for k in batch.kmers).encode("ascii")
+    pos = np.ascontiguousarray(batch.tx_pos, dtype=np.int64)
+    ro = np.ascontiguousarray(batch.read_off, dtype=np.int64)
+    sp = np.ascontiguousarray(site_prob, dtype=np.float32)
+    mc = np.ascontiguousarray(mod_count, dtype=np.int32)
+    _cabi.check(_cabi.lib().m6a_write_site_csv(f.fileno(), batch.n_sites, tx, _vp(off), _vp(pos), _vp(ro), _vp(sp), _vp(mc),
+                                               kmer5, n_threads), "m6a_write_site_csv")
 
 
-def _worker_init(ds):
-    global _WORKER_DS
-    _WORKER_DS = ds
-
-
-def _worker_load(span):
-    return _WORKER_DS.load_sites(*span)
-
-
-def _concat_batches(parts: List[SiteBatch]) -> SiteBatch:
-    if len(parts) == 1:
-        return parts[0]
-    offs, base = [np.zeros(1, np.int64)], 0
-    for p in parts:
-        offs.append(p.read_off[1:] + base)
-        base += int(p.read_off[-1])
-    return SiteBatch(np.concatenate([p.feats for p in parts]), np.concatenate(offs), np.concatenate([p.kmer_idx for p in parts]),
-                     np.concatenate([p.read_ids for p in parts]), np.concatenate([p.tx_ids for p in parts]),
-                     np.concatenate([p.tx_pos for p in parts]), np.concatenate([p.kmers for p in parts]))
+def write_indiv_rows(g, batch: SiteBatch, read_prob: np.ndarray, n_threads: int = 0):
+    """'%s,%d,%s,%.16f' rows (tx_id, tx_pos, read_index, read_prob) (reference utils/inference_utils.py:63-64);
+    read_index is the integer id, or "{id}_{replicate}" for multi-directory input (utils/data_utils.py:421-423)."""
+    from . import _cabi
+    g.flush()
+    tx, off = _tx_buffer(batch.tx_ids)
+    pos = np.ascontiguousarray(batch.tx_pos, dtype=np.int64)
+    ro = np.ascontiguousarray(batch.read_off, dtype=np.int64)
+    ids = np.ascontiguousarray(batch.read_ids, dtype=np.int64)
+    rep = None if batch.read_rep is None else np.ascontiguousarray(batch.read_rep, dtype=np.int32)
+    rp = np.ascontiguousarray(read_prob, dtype=np.float32)
+    _cabi.check(_cabi.lib().m6a_write_indiv_csv(g.fileno(), batch.n_sites, tx, _vp(off), _vp(pos), _vp(ro), _vp(ids),
+                                                None if rep is None else _vp(rep), _vp(rp), n_threads), "m6a_write_indiv_csv")
 
 
 def plan_batches(n_reads: np.ndarray, lo: int, hi: int, reads_per_batch: int) -> List[tuple]:
@@ -165,36 +162,23 @@ def run_inference(model: MILModel, dl, args):
     bounds = shard_bounds(ds.n_reads, world)
     lo, hi = bounds[rank], bounds[rank + 1]
     spans = plan_batches(ds.n_reads, lo, hi, reads_per_batch)
-    n_workers = max(1, min(int(getattr(args, "n_processes", 1)), os.cpu_count() or 1))
-    sub = max(1, 256)   # sites per ingest task
+    n_threads = max(1, min(int(getattr(args, "n_processes", 1)), os.cpu_count() or 1))   # ingest / CSV worker threads
 
     site_path = os.path.join(args.out_dir, "data.site_proba.csv")
     indiv_path = os.path.join(args.out_dir, "data.indiv_proba.csv")
     suffix = f".rank{rank}" if world > 1 else ""
     all_sp, all_mc = [], []
-    pool = None
-    if n_workers > 1 and len(spans):
-        # ingest workers are forked before the CUDA context exists; they only parse JSON
-        pool = ProcessPoolExecutor(n_workers, mp_context=multiprocessing.get_context("fork"), initializer=_worker_init,
-                                   initargs=(ds,))
-        list(pool.map(_worker_load, [(lo, lo)] * n_workers))
     eng = model.engine(dev)
-    try:
-        with open(site_path + suffix, 'a', encoding='utf-8') as f, open(indiv_path + suffix, 'a', encoding='utf-8') as g:
-            for a, b in spans:
-                tasks = [(s, min(s + sub, b)) for s in range(a, b, sub)]
-                parts = list(pool.map(_worker_load, tasks)) if pool is not None else [ds.load_sites(*t) for t in tasks]
-                batch = _concat_batches(parts)
-                read_prob, site_prob, mod_count = eng.infer_host(batch.feats, batch.read_off, batch.kmer_idx, n_iters,
-                                                                 seed=seed, site_id_base=a, n_samples=N_SAMPLES,
-                                                                 read_threshold=thr)
-                write_site_rows(f, batch, site_prob, mod_count)
-                write_indiv_rows(g, batch, read_prob)
-                all_sp.append(site_prob)
-                all_mc.append(mod_count)
-    finally:
-        if pool is not None:
-            pool.shutdown()
+    with open(site_path + suffix, 'ab') as f, open(indiv_path + suffix, 'ab') as g:
+        for a, b in spans:
+            batch = ds.load_sites(a, b, n_threads=n_threads)                      # data.json -> flat buffers (native)
+            read_prob, site_prob, mod_count = eng.infer_host(batch.feats, batch.read_off, batch.kmer_idx, n_iters,
+                                                             seed=seed, site_id_base=a, n_samples=N_SAMPLES,
+                                                             read_threshold=thr)    # H2D -> kernel -> D2H
+            write_site_rows(f, batch, site_prob, mod_count, n_threads)
+            write_indiv_rows(g, batch, read_prob, n_threads)
+            all_sp.append(site_prob)
+            all_mc.append(mod_count)
     site_prob = np.concatenate(all_sp) if all_sp else np.zeros(0, np.float32)
     mod_count = np.concatenate(all_mc) if all_mc else np.zeros(0, np.int32)
 

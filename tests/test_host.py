@@ -109,9 +109,12 @@ def test_replicate_dataset_pools_sites(bundled_dir, tmp_path, bundled_flat):
     assert ds.n_reads[0] == 662 and ds.n_reads[1] == 882
     b = ds.load_sites(0, 2)
     assert list(np.diff(b.read_off)) == [662, 882]
-    assert b.read_ids[0].endswith("_0") and b.read_ids[662 + 441].endswith("_1") and b.read_ids[662 + 441].split("_")[0] == b.read_ids[662].split("_")[0]
+    assert b.read_rep[0] == 0 and b.read_rep[662 + 441] == 1 and b.read_ids[662 + 441] == b.read_ids[662]
     s1 = single.load_sites(1, 2)
     assert np.array_equal(b.feats[662:662 + 441], s1.feats) and np.array_equal(b.feats[662 + 441:], s1.feats)
+    # reference-shaped item: "{read_id}_{replicate}" strings, same features as the flat path
+    feats, kmers, tx, pos, rid = ds[1]
+    assert np.array_equal(feats, b.feats[662:]) and rid[0] == f"{b.read_ids[662]}_0" and rid[441] == f"{b.read_ids[662]}_1"
 
 
 def test_csv_row_formats_match_reference(bundled_flat):
@@ -120,13 +123,39 @@ def test_csv_row_formats_match_reference(bundled_flat):
     from m6anet_b200.inference import write_indiv_rows, write_site_rows
     batch = SiteBatch(np.zeros((3, 9), np.float32), np.array([0, 2, 3]), np.zeros((2, 3), np.int32), np.array([966210, 7, 8]),
                       np.array(["ENST1.5", "ENST2"]), np.array([130, 7]), np.array(["GGACT", "AAACA"]))
-    f, g = io.StringIO(), io.StringIO()
-    write_site_rows(f, batch, np.array([0.25, np.float32(0.1)], np.float32), np.array([1, 0], np.int32))
-    write_indiv_rows(g, batch, np.array([0.5, 0.125, np.float32(1e-20)], np.float32))
-    assert f.getvalue().splitlines()[0] == "ENST1.5,130,2,0.2500000000000000,GGACT,0.5000000000000000"
-    assert f.getvalue().splitlines()[1] == "ENST2,7,1,%.16f,AAACA,0.0000000000000000" % float(np.float32(0.1))
-    assert g.getvalue().splitlines() == ["ENST1.5,130,966210,0.5000000000000000", "ENST1.5,130,7,0.1250000000000000",
-                                         "ENST2,7,8,0.0000000000000000"]
+    import tempfile
+    with tempfile.TemporaryFile("w+b") as f, tempfile.TemporaryFile("w+b") as g, tempfile.TemporaryFile("w+b") as h:
+        write_site_rows(f, batch, np.array([0.25, np.float32(0.1)], np.float32), np.array([1, 0], np.int32))
+        write_indiv_rows(g, batch, np.array([0.5, 0.125, np.float32(1e-20)], np.float32))
+        batch.read_rep = np.array([0, 1, 1], np.int32)
+        write_indiv_rows(h, batch, np.array([0.5, 0.125, 1.0], np.float32))
+        f.seek(0), g.seek(0), h.seek(0)
+        fl, gl, hl = f.read().decode().splitlines(), g.read().decode().splitlines(), h.read().decode().splitlines()
+    assert fl[0] == "ENST1.5,130,2,0.2500000000000000,GGACT,0.5000000000000000"
+    assert fl[1] == "ENST2,7,1,%.16f,AAACA,0.0000000000000000" % float(np.float32(0.1))
+    assert gl == ["ENST1.5,130,966210,0.5000000000000000", "ENST1.5,130,7,0.1250000000000000", "ENST2,7,8,0.0000000000000000"]
+    assert hl == ["ENST1.5,130,966210_0,0.5000000000000000", "ENST1.5,130,7_1,0.1250000000000000", "ENST2,7,8_1,1.0000000000000000"]
+    # many rows, random values: identical to Python's own '%' formatting (what the reference executes)
+    rng = np.random.default_rng(0)
+    S = 2000
+    n = rng.integers(1, 40, S)
+    off = np.concatenate([[0], np.cumsum(n)])
+    big = SiteBatch(np.zeros((off[-1], 9), np.float32), off, np.zeros((S, 3), np.int32), rng.integers(0, 10**7, off[-1]),
+                    np.array([f"ENST{rng.integers(10**10)}.{i % 9}" for i in range(S)]), rng.integers(0, 10**5, S),
+                    rng.choice(["GGACT", "AAACA", "TGACC"], S))
+    rp = np.exp(rng.uniform(-50, 0, off[-1])).astype(np.float32)
+    sp = rng.random(S).astype(np.float32)
+    mc = np.minimum(rng.integers(0, 40, S), n).astype(np.int32)
+    with tempfile.TemporaryFile("w+b") as f, tempfile.TemporaryFile("w+b") as g:
+        write_site_rows(f, big, sp, mc, n_threads=4)
+        write_indiv_rows(g, big, rp, n_threads=4)
+        f.seek(0), g.seek(0)
+        fl, gl = f.read().decode(), g.read().decode()
+    want_f = "".join('%s,%d,%s,%.16f,%s,%.16f\n' % (t, p, k, float(a), km, m / k) for t, p, k, a, km, m in
+                     zip(big.tx_ids, big.tx_pos, n, sp, big.kmers, mc.astype(np.float64)))
+    want_g = "".join('%s,%d,%s,%.16f\n' % (t, p, r, float(a)) for t, p, r, a in
+                     zip(np.repeat(big.tx_ids, n), np.repeat(big.tx_pos, n), big.read_ids, rp))
+    assert fl == want_f and gl == want_g
 
 
 def test_argparser_keeps_reference_flags():
@@ -163,3 +192,60 @@ def test_shard_bounds_balance_reads():
     spans = plan_batches(n, 100, 4000, 50_000)
     assert spans[0][0] == 100 and spans[-1][1] == 4000 and all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
     assert all(n[a:b].sum() < 50_000 + 1000 for a, b in spans)
+
+
+def test_native_ingest_equals_python_path_and_handles_number_formats(tmp_path):
+    """m6a_ingest_parts vs the per-site Python/json path on a hand-written data.json: exponents, negatives,
+    integers, 9-mer context (two flanks in the file, one wanted), every DRACH k-mer id."""
+    import json
+    from m6anet_b200 import constants as C
+    from m6anet_b200.data import NanopolishDS
+    rng = np.random.default_rng(5)
+    lines, info, off = [], ["transcript_id,transcript_position,start,end,n_reads"], 0
+    seven = ["GGGACTT", "AAAACAA", "TTGACTG", "CAGACCA"]
+    fmt = [lambda v: repr(float(v)), lambda v: "%.3e" % v, lambda v: "%.12f" % v, lambda v: str(int(v * 100))]
+    for i, k in enumerate(seven * 3):
+        n = int(rng.integers(20, 60))
+        rows = []
+        for r in range(n):
+            vals = rng.normal([0.01, 3, 110] * 3, [0.005, 1.5, 8] * 3)
+            vals[0] = -abs(vals[0]) if r == 0 else vals[0]
+            txt = ",".join(fmt[(r + c) % 4](v) for c, v in enumerate(vals)) + "," + repr(float(rng.integers(1, 10**6)))
+            rows.append("[" + txt + "]")
+        line = '{"tx%d":{"%d":{"%s":[%s]}}}\n' % (i, 100 + i, k, ",".join(rows))
+        json.loads(line)
+        info.append(f"tx{i},{100 + i},{off},{off + len(line)},{n}")
+        off += len(line)
+        lines.append(line)
+    (tmp_path / "data.json").write_text("".join(lines))
+    (tmp_path / "data.info").write_text("\n".join(info) + "\n")
+    ds = NanopolishDS(str(tmp_path), 20, C.DEFAULT_NORM_PATH)
+    flat = ds.load_sites(0, len(ds), n_threads=3)
+    for i in range(len(ds)):
+        feats, kmers, tx, pos, rid = ds[i]                       # Python json path (reference-shaped)
+        sl = slice(flat.read_off[i], flat.read_off[i + 1])
+        assert np.array_equal(flat.feats[sl], feats) and np.array_equal(flat.read_ids[sl], rid)
+        assert np.array_equal(flat.kmer_idx[i], kmers[0]) and flat.kmers[i] == seven[i % 4][1:6]
+    # partial ranges and an empty range
+    part = ds.load_sites(3, 7)
+    assert np.array_equal(part.feats, flat.feats[flat.read_off[3]:flat.read_off[7]]) and part.n_sites == 4
+    assert ds.load_sites(5, 5).n_sites == 0
+
+
+def test_native_ingest_reports_bad_input(tmp_path):
+    from m6anet_b200 import constants as C
+    from m6anet_b200._cabi import M6AError
+    from m6anet_b200.data import NanopolishDS
+    row = "[" + ",".join(["1.0"] * 9) + ",7.0]"
+    line = '{"t":{"5":{"GGGACTT":[%s]}}}\n' % ",".join([row] * 20)
+    (tmp_path / "data.json").write_text(line)
+    (tmp_path / "data.info").write_text(f"transcript_id,transcript_position,start,end,n_reads\nt,5,0,{len(line)},21\n")
+    ds = NanopolishDS(str(tmp_path), 20, C.DEFAULT_NORM_PATH)
+    with pytest.raises(M6AError, match="t:5"):                   # data.info says 21 reads, the line has 20
+        ds.load_sites(0, 1)
+    (tmp_path / "data.info").write_text(f"transcript_id,transcript_position,start,end,n_reads\nt,5,0,{len(line)},20\n")
+    assert NanopolishDS(str(tmp_path), 20, C.DEFAULT_NORM_PATH).load_sites(0, 1).feats.shape == (20, 9)
+    with pytest.raises(M6AError):                                # arabidopsis norm factors lack most 5-mers of HCT116 data? use a non-DRACH k-mer
+        bad = line.replace("GGGACTT", "GGGTCTT")
+        (tmp_path / "data.json").write_text(bad)
+        NanopolishDS(str(tmp_path), 20, C.DEFAULT_NORM_PATH).load_sites(0, 1)
