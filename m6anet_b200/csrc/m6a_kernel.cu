@@ -39,6 +39,7 @@ struct Smem {
   int roff[kSitesPerTileMax + 1];
   int cnt[kSitesPerTileMax];
   int kid[kSitesPerTileMax][kKmerPos];
+  alignas(8) long long r0_next;          // first feature row of the CTA's next tile (header prefetch)
   alignas(8) unsigned long long bar_w;
   alignas(8) unsigned long long bar_f;
 };
@@ -128,6 +129,30 @@ __device__ __forceinline__ float mc_lane_generic(const float* qbase, bool from_p
   return v;
 }
 
+// ---- feature staging geometry: rows [r0 + chunk*kChunkReads, ...) of feats as 16-byte granules -----------
+struct Span {
+  unsigned long long b0, b1;   // exact byte range of the rows
+  unsigned long long g0, g1;   // granule range moved by the bulk copy (g1 clamped to the buffer's last full granule)
+};
+__device__ __forceinline__ Span chunk_span(const KernelArgs& a, long long r0, int nr, int chunk) {
+  Span sp;
+  const long long ra = r0 + static_cast<long long>(chunk) * kChunkReads;
+  const int rows = min(kChunkReads, nr - chunk * kChunkReads);
+  sp.b0 = static_cast<unsigned long long>(ra) * (kNSig * 4);
+  sp.b1 = sp.b0 + static_cast<unsigned long long>(rows) * (kNSig * 4);
+  sp.g0 = sp.b0 & ~15ull;
+  sp.g1 = (sp.b1 + 15ull) & ~15ull;
+  const unsigned long long gend = a.feats_bytes & ~15ull;
+  if (sp.g1 > gend) sp.g1 = gend;
+  return sp;
+}
+// chunk 0 of a tile can be staged ahead of time iff one bulk copy covers it completely
+__device__ __forceinline__ bool chunk0_prefetchable(const KernelArgs& a, long long r0, int nr) {
+  if (!a.feats_tma_ok || nr <= 0) return false;
+  const Span sp = chunk_span(a, r0, nr, 0);
+  return sp.g1 > sp.g0 && sp.b1 <= sp.g1;
+}
+
 // -------------------------------------------------------------------------------------------------
 template <int NS>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -157,42 +182,47 @@ mil_infer_kernel(const KernelArgs a) {
   const bool tma_ok = a.feats_tma_ok;
   const float n_iters_f = static_cast<float>(a.n_iters);
 
+  // header prefetch state (registers): this thread's CSR offset and k-mer ids of the CTA's NEXT tile
+  bool pf_valid = false;
+  long long pf_off = 0;
+  int pf_kid[kKmerPos] = {0, 0, 0};
+
   for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const long long s0 = tile * a.sites_per_tile;
     const int ns = static_cast<int>(min(static_cast<long long>(a.sites_per_tile), a.n_sites - s0));
-    const long long r0 = a.read_off[s0];
 
     // ---- tile header: local CSR offsets, k-mer ids, counters ------------------------------------
-    if (tid <= ns) sm.roff[tid] = static_cast<int>(a.read_off[s0 + tid] - r0);
+    // (prefetched during the previous tile's phase B; plain global loads for the CTA's first tile)
+    long long my_off = pf_off;
+    int my_kid[kKmerPos] = {pf_kid[0], pf_kid[1], pf_kid[2]};
+    long long r0;
+    if (pf_valid) {
+      r0 = sm.r0_next;                         // written by thread 0 before the previous tile's closing barrier
+    } else {
+      r0 = a.read_off[s0];
+      if (tid <= ns) my_off = a.read_off[s0 + tid];
+      if (tid < ns && a.kmer_idx != nullptr) {
+#pragma unroll
+        for (int t = 0; t < kKmerPos; ++t) my_kid[t] = a.kmer_idx[(s0 + tid) * kKmerPos + t];
+      }
+    }
+    if (tid <= ns) sm.roff[tid] = static_cast<int>(my_off - r0);
     if (tid < ns) {
       sm.cnt[tid] = 0;
 #pragma unroll
-      for (int t = 0; t < kKmerPos; ++t) {
-        int k = a.kmer_idx != nullptr ? a.kmer_idx[(s0 + tid) * kKmerPos + t] : 0;
-        k = (a.model.n_kmer == 1) ? 0 : min(max(k, 0), a.model.n_kmer - 1);
-        sm.kid[tid][t] = k;
-      }
+      for (int t = 0; t < kKmerPos; ++t)
+        sm.kid[tid][t] = (a.model.n_kmer == 1 || a.kmer_idx == nullptr) ? 0 : min(max(my_kid[t], 0), a.model.n_kmer - 1);
     }
     __syncthreads();
     const int nr = sm.roff[ns];                 // reads in this tile
     const bool q_in_smem = nr <= kQCap;
     const int n_chunks = (nr + kChunkReads - 1) / kChunkReads;
+    const bool chunk0_staged = pf_valid && chunk0_prefetchable(a, r0, nr);   // same predicate thread 0 used when it issued it
 
     // ---- feature staging: rows [ra, ra+rows) of feats -> sm.feat[head + i*9 + k] ---------------------
-    auto chunk_span = [&](int chunk, unsigned long long& b0, unsigned long long& b1, unsigned long long& g0,
-                          unsigned long long& g1) {
-      const long long ra = r0 + static_cast<long long>(chunk) * kChunkReads;
-      const int rows = min(kChunkReads, nr - chunk * kChunkReads);
-      b0 = static_cast<unsigned long long>(ra) * (kNSig * 4);
-      b1 = b0 + static_cast<unsigned long long>(rows) * (kNSig * 4);
-      g0 = b0 & ~15ull;                                   // 16-byte granules for the bulk copy
-      g1 = (b1 + 15ull) & ~15ull;
-      const unsigned long long gend = a.feats_bytes & ~15ull;
-      if (g1 > gend) g1 = gend;
-    };
     auto stage_chunk = [&](int chunk) {
-      unsigned long long b0, b1, g0, g1;
-      chunk_span(chunk, b0, b1, g0, g1);
+      const Span sp = chunk_span(a, r0, nr, chunk);
+      const unsigned long long b0 = sp.b0, b1 = sp.b1, g0 = sp.g0, g1 = sp.g1;
       if (tma_ok) {
         if (tid == 0 && g1 > g0) {
           mbar_expect_tx(&sm.bar_f, static_cast<uint32_t>(g1 - g0));
@@ -211,17 +241,30 @@ mil_infer_kernel(const KernelArgs a) {
       }
     };
 
-    if (n_chunks > 0) stage_chunk(0);
+    if (n_chunks > 0 && !chunk0_staged) stage_chunk(0);
 
-    // c_site[s][j] = ctab0[k0][j] + ctab1[k1][j] + ctab2[k2][j]   (coalesced over j, L2 resident)
+    // c_site[s][j] = ctab0[k0][j] + ctab1[k1][j] + ctab2[k2][j]   (coalesced over j, L2 resident).
+    // Four elements per thread per batch, all 12 loads issued before the first add: one L2 round trip per batch.
     {
       const float* ctab = a.model.ctab;
       const size_t tstride = static_cast<size_t>(a.model.n_kmer) * kH1Max;
-      for (int i = tid; i < ns * kH1Max; i += kThreads) {
-        const int s = i / kH1Max, j = i - s * kH1Max;
-        sm.csite[s][j] = __ldg(ctab + static_cast<size_t>(sm.kid[s][0]) * kH1Max + j) +
-                         __ldg(ctab + tstride + static_cast<size_t>(sm.kid[s][1]) * kH1Max + j) +
-                         __ldg(ctab + 2 * tstride + static_cast<size_t>(sm.kid[s][2]) * kH1Max + j);
+      const int total = ns * kH1Max;
+      for (int base = 0; base < total; base += 4 * kThreads) {
+        float v[4][3];
+        int at[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = base + u * kThreads + tid;
+          const bool ok = i < total;
+          const int s = ok ? i / kH1Max : 0, j = ok ? i - s * kH1Max : 0;
+          at[u] = ok ? s * kCStride + j : -1;
+#pragma unroll
+          for (int t = 0; t < kKmerPos; ++t)
+            v[u][t] = ok ? __ldg(ctab + t * tstride + static_cast<size_t>(sm.kid[s][t]) * kH1Max + j) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (at[u] >= 0) (&sm.csite[0][0])[at[u]] = (v[u][0] + v[u][1]) + v[u][2];
       }
     }
     if (!weights_ready) {
@@ -231,8 +274,8 @@ mil_infer_kernel(const KernelArgs a) {
 
     // ---- phase A: read encoder ---------------------------------------------------------------------
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
-      unsigned long long b0, b1, g0, g1;
-      chunk_span(chunk, b0, b1, g0, g1);
+      const Span csp = chunk_span(a, r0, nr, chunk);
+      const unsigned long long b0 = csp.b0, g0 = csp.g0, g1 = csp.g1;
       if (tma_ok && g1 > g0) {
         mbar_wait(&sm.bar_f, f_parity);
         f_parity ^= 1u;
@@ -328,11 +371,29 @@ mil_infer_kernel(const KernelArgs a) {
     }
     __syncthreads();  // q, cnt and (fallback) read_prob of the whole tile are visible
 
+    // ---- prefetch the header of this CTA's next tile: the loads fly during phase B ---------------------------
+    const long long tile_n = tile + gridDim.x;
+    const bool has_next = tile_n < a.n_tiles;
+    long long pf_end = 0;                         // thread 0: one past the last feature row of the next tile
+    if (has_next) {
+      const long long s0n = tile_n * a.sites_per_tile;
+      const int nsn = static_cast<int>(min(static_cast<long long>(a.sites_per_tile), a.n_sites - s0n));
+      if (tid <= nsn) pf_off = a.read_off[s0n + tid];
+      if (tid < nsn && a.kmer_idx != nullptr) {
+#pragma unroll
+        for (int t = 0; t < kKmerPos; ++t) pf_kid[t] = a.kmer_idx[(s0n + tid) * kKmerPos + t];
+      }
+      if (tid == 0) pf_end = a.read_off[s0n + nsn];
+    }
+    pf_valid = has_next;
+
     // ---- phase B: Monte-Carlo noisy-OR ----------------------------------------------------------
     {
+      // items (site, block) are dealt round-robin to the warps; (sl, blk) advance without a division
       const int items = ns * n_blocks;
+      int sl = 0, blk = warp;
+      while (blk >= n_blocks) { blk -= n_blocks; ++sl; }
       for (int item = warp; item < items; item += kWarps) {
-        const int sl = item / n_blocks, blk = item - sl * n_blocks;
         const int n = sm.roff[sl + 1] - sm.roff[sl];
         float v = 0.0f;
         if (n > 0) {
@@ -356,6 +417,20 @@ mil_infer_kernel(const KernelArgs a) {
         }
         v = warp_butterfly_sum(v);
         if (lane == 0) sm.partial[sl][blk] = v;
+        blk += kWarps;
+        while (blk >= n_blocks) { blk -= n_blocks; ++sl; }
+      }
+    }
+    // The feature buffer is idle since the last chunk went to registers: stage the next tile's first chunk now,
+    // so that the copy overlaps the barriers, the finalize step and the next c_site gather.
+    if (tid == 0 && has_next) {
+      sm.r0_next = pf_off;
+      const int nrn = static_cast<int>(pf_end - pf_off);
+      if (chunk0_prefetchable(a, pf_off, nrn)) {
+        const Span sp = chunk_span(a, pf_off, nrn, 0);
+        mbar_expect_tx(&sm.bar_f, static_cast<uint32_t>(sp.g1 - sp.g0));
+        bulk_g2s(sm.feat, reinterpret_cast<const unsigned char*>(a.feats) + sp.g0, static_cast<uint32_t>(sp.g1 - sp.g0),
+                 &sm.bar_f);
       }
     }
     __syncthreads();

@@ -193,3 +193,19 @@ def test_torch_port_used_for_cpu_timing_equals_numpy_restatement(synthetic_input
         b = read_probabilities_torch(params, si["feats"], kmer_rows)
         assert np.max(np.abs(a - b)) <= 2e-6
         assert np.array_equal(b, load_golden(tag)["read_prob"])   # identical calls to the reference => identical bits
+
+
+def test_c_restatement_equals_numpy_oracle(synthetic_inputs):
+    """oracle/c (used to check every site of full-size jobs) against the NumPy restatement and the reference goldens."""
+    from oracle import c_oracle
+    si = synthetic_inputs
+    for seed, site, n in [(0, 0, 20), (1234, 7_000_000_123, 50), (2**63 + 5, 2**40 + 1, 4001)]:
+        assert np.array_equal(c_oracle.sample_indices(seed, site, n, 2100, 20).astype(np.int64), sample_indices(seed, site, n, 2100, 20))
+    for tag in ("HCT116_RNA002", "signal_only"):
+        g = load_golden(tag)
+        kw = dict(n_iters=int(g["n_iters"]), seed=int(g["seed"]), site_id_base=int(g["site_id_base"]), n_samples=20,
+                  read_threshold=float(g["threshold"]))
+        rp, sp, mc = c_oracle.mil_inference(oracle_params(tag), si["feats"], si["read_off"], si["kmer_idx"], **kw)
+        assert np.max(np.abs(rp - g["read_prob"])) <= 2e-6
+        assert np.max(np.abs(sp - g["site_prob"])) <= 1e-5          # reference literal MIL forward on the shared stream
+        assert np.array_equal(mc, g["mod_count"])
