@@ -373,7 +373,7 @@ mil_infer_kernel(const KernelArgs a) {
 
     // ---- prefetch the header of this CTA's next tile: the loads fly during phase B ---------------------------
     const long long tile_n = tile + gridDim.x;
-    const bool has_next = tile_n < a.n_tiles;
+    const bool has_next = (M6A_PREFETCH != 0) && tile_n < a.n_tiles;
     long long pf_end = 0;                         // thread 0: one past the last feature row of the next tile
     if (has_next) {
       const long long s0n = tile_n * a.sites_per_tile;

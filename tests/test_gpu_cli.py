@@ -112,3 +112,25 @@ def test_cli_entry_point(bundled_dir, tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     site = pd.read_csv(tmp_path / "data.site_proba.csv")
     assert len(site) == 101 and site["probability_modified"].between(0, 1).all()
+
+
+def test_two_gpu_cli_equals_single_gpu(bundled_dir, tmp_path):
+    """torchrun with 2 ranks: site shards + one all-gather + rank-ordered CSV concatenation give byte-identical files."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from m6anet_b200 import inference
+    one = tmp_path / "one"
+    inference.main(inference_args([bundled_dir], one, num_iterations=1000))
+    two = tmp_path / "two"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29631", "-m", "m6anet_b200", "inference", "--input_dir", bundled_dir,
+                        "--out_dir", str(two), "--num_iterations", "1000", "--n_processes", "4"],
+                       cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for name in ("data.site_proba.csv", "data.indiv_proba.csv"):
+        assert open(one / name).read() == open(two / name).read()
+    assert not [f for f in os.listdir(two) if ".rank" in f]
