@@ -233,6 +233,20 @@ def test_invalid_arguments_are_rejected(synthetic_inputs):
         MilEngine(bad, "cuda:0")
 
 
+def _read_probs_float64(params, feats, kmer_rows):
+    """The read encoder of oracle.read_probabilities evaluated in float64 (exact to ~1e-15): the yardstick for float32 error."""
+    f64 = np.float64
+    x = feats.astype(f64)
+    if params.emb is not None:
+        x = np.concatenate([x, params.emb.astype(f64)[kmer_rows].reshape(-1, 3 * params.emb.shape[1])], axis=1)
+    h = x @ params.w1.astype(f64).T + params.b1
+    h = (h - params.bn_mean) / np.sqrt(params.bn_var.astype(f64) + params.bn_eps) * params.bn_gamma + params.bn_beta
+    h = np.maximum(h, 0)
+    h = np.maximum(h @ params.w2.astype(f64).T + params.b2, 0)
+    z = h @ params.w3.astype(f64).reshape(-1) + float(params.b3.reshape(-1)[0])
+    return 1.0 / (1.0 + np.exp(-z))
+
+
 def _full_size_check(tag, n_sites, n_reads, thr, seed=0, site_id_base=0, pooled_from=1):
     """Run a BASELINE-size config and check EVERY site against the C restatement of the oracle on the shared index
     stream, plus size-independent properties (determinism, closed-form expectation)."""
@@ -247,7 +261,11 @@ def _full_size_check(tag, n_sites, n_reads, thr, seed=0, site_id_base=0, pooled_
     rp2, sp2, mc2 = run_device(eng, feats, off, kmer, 1000, **kw)
     assert np.array_equal(rp, rp2) and np.array_equal(sp, sp2) and np.array_equal(mc, mc2)      # idempotent
     orp, osp, omc = c_oracle.mil_inference(oracle_params(tag), feats, off, kmer, 1000, n_samples=20, **kw)
-    assert np.max(np.abs(rp - orp)) <= READ_ATOL
+    # Over millions of reads the float32 evaluations (the reference's torch calls included) each sit up to ~1.9e-6 from
+    # the exact value, so two of them can differ by more than READ_ATOL; the kernel is held to the float64 truth instead.
+    truth = _read_probs_float64(oracle_params(tag), feats, np.repeat(kmer, n_reads, axis=0))
+    assert np.max(np.abs(rp - truth)) <= 3e-6
+    assert np.max(np.abs(rp - orp)) <= 5e-6
     assert np.max(np.abs(sp - osp)) <= SITE_ATOL                                               # every site
     near = np.abs(orp.astype(np.float64) - float(np.float32(thr))) < 1e-6
     slack = np.add.reduceat(near.astype(np.int64), off[:-1])
