@@ -56,12 +56,14 @@ def parse_args():
     ap.add_argument("--cpu-sample-sites", type=int, default=20_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ragged", action="store_true", help="robustness run: lognormal n_reads (median 33, clip [20, 1000]) "
+                    "instead of the constant --reads of the headline job (SURVEY.md section 8d)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return (f"synthetic {a.sites} DRACH sites x {a.reads} reads, {a.model}, num_iterations={a.iters}, "
-            f"20 reads/bag, site-sharded")
+    reads = "ragged reads (lognormal, median 33, 20..1000)" if a.ragged else f"{a.reads} reads"
+    return f"synthetic {a.sites} DRACH sites x {reads}, {a.model}, num_iterations={a.iters}, 20 reads/bag, site-sharded"
 
 
 def algorithmic_bytes_per_site(n_reads: int) -> int:
@@ -69,10 +71,15 @@ def algorithmic_bytes_per_site(n_reads: int) -> int:
     return n_reads * 36 + 12 + 8 + n_reads * 4 + 8
 
 
-def synth_shard(site_a: int, site_b: int, n_reads: int, seed_tag: int):
+def synth_shard(site_a: int, site_b: int, n_reads: int, seed_tag: int, ragged: bool = False):
     """Synthetic shard [site_a, site_b): N(0,1) features, uniform valid k-mer ids."""
     rng = np.random.default_rng([0, seed_tag, site_a])
     ns = site_b - site_a
+    if ragged:
+        n = np.clip(np.round(np.exp(rng.normal(np.log(33), 0.8, size=ns))), 20, 1000).astype(np.int64)
+        read_off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+        feats = rng.standard_normal((int(read_off[-1]), 9), dtype=np.float32)
+        return feats, read_off, rng.integers(0, 66, size=(ns, 3), dtype=np.int32)
     feats = rng.standard_normal((ns * n_reads, 9), dtype=np.float32)
     read_off = np.arange(ns + 1, dtype=np.int64) * n_reads
     kmer = rng.integers(0, 66, size=(ns, 3), dtype=np.int32)
@@ -205,7 +212,7 @@ def main():
     sa, sb = bounds[rank], bounds[rank + 1]
     ns = sb - sa
     shard_max = max(bounds[r + 1] - bounds[r] for r in range(world))
-    feats_h, off_h, kmer_h = synth_shard(sa, sb, a.reads, 1)
+    feats_h, off_h, kmer_h = synth_shard(sa, sb, a.reads, 1, a.ragged)
     thr = MODELS[a.model][1]
     eng = MilEngine(W.from_npz(os.path.join(ROOT, "m6anet_b200", "assets", "model_states", MODELS[a.model][0])), dev)
 
@@ -268,7 +275,7 @@ def main():
     # ---- roofline of the fused kernel (this rank's launches; algorithmic bytes / CUDA-event time) -----
     peak, peak_src = peaks()
     k_avg_ms = sum(kernel_ms) / len(kernel_ms)
-    alg_bytes = ns * algorithmic_bytes_per_site(a.reads)
+    alg_bytes = int(feats_h.shape[0]) * 40 + ns * 28 if a.ragged else ns * algorithmic_bytes_per_site(a.reads)
     achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -319,10 +326,10 @@ def main():
         from oracle.cpu_baseline import host_cores, time_reference_port
         params = ReadEncoderParams.from_npz(os.path.join(ROOT, "m6anet_b200", "assets", "model_states", MODELS[a.model][0]))
         n_sample = min(a.sites, a.cpu_sample_sites)
-        r = time_reference_port(params, feats_h[: n_sample * a.reads], off_h[: n_sample + 1], kmer_h[:n_sample], a.iters,
+        r = time_reference_port(params, feats_h[: int(off_h[n_sample])], off_h[: n_sample + 1], kmer_h[:n_sample], a.iters,
                                 n_procs=host_cores(), read_threshold=thr)
         cpu = {"value": r["sites_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"first {n_sample} sites of the job ({n_sample * a.reads} reads), encoder {r['t_encoder_s']:.3f}s "
+               "sample": f"first {n_sample} sites of the job ({int(off_h[n_sample])} reads), encoder {r['t_encoder_s']:.3f}s "
                          f"+ MC Pool({r['cores']}) {r['t_mc_s']:.3f}s"}
 
     if rank == 0:

@@ -153,6 +153,75 @@ __device__ __forceinline__ bool chunk0_prefetchable(const KernelArgs& a, long lo
   return sp.g1 > sp.g0 && sp.b1 <= sp.g1;
 }
 
+// ---- read encoder for R reads per thread (R = 2 full chunk rows, R = 1 for a warp whose second slot is empty) --
+template <int R>
+__device__ __forceinline__ void encode_reads(Smem& sm, const KernelArgs& a, const float (&x)[kReadsPerThread][kNSig],
+                                             const float* const (&cs)[kReadsPerThread], const int (&site_l)[kReadsPerThread],
+                                             const bool (&valid)[kReadsPerThread], long long r0, int cbase, int tid,
+                                             int n_pairs, bool q_in_smem) {
+  float2 acc[R][kH2 / 2];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < kH2 / 2; ++k) acc[r][k] = make_float2(sm.w.b2[2 * k], sm.w.b2[2 * k + 1]);
+
+#pragma unroll 1
+  for (int p = 0; p < n_pairs; ++p) {
+    const float4* wp = reinterpret_cast<const float4*>(sm.w.pair[p]);
+    const float4 u0 = wp[0], u1 = wp[1], u2 = wp[2], u3 = wp[3], u4 = wp[4];
+    float2 h[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 t = *reinterpret_cast<const float2*>(cs[r] + 2 * p);
+      t = ffma2(make_float2(u0.x, u0.y), x[r][0], t);
+      t = ffma2(make_float2(u0.z, u0.w), x[r][1], t);
+      t = ffma2(make_float2(u1.x, u1.y), x[r][2], t);
+      t = ffma2(make_float2(u1.z, u1.w), x[r][3], t);
+      t = ffma2(make_float2(u2.x, u2.y), x[r][4], t);
+      t = ffma2(make_float2(u2.z, u2.w), x[r][5], t);
+      t = ffma2(make_float2(u3.x, u3.y), x[r][6], t);
+      t = ffma2(make_float2(u3.z, u3.w), x[r][7], t);
+      t = ffma2(make_float2(u4.x, u4.y), x[r][8], t);
+      h[r] = make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f));
+    }
+#pragma unroll
+    for (int k4 = 0; k4 < kH2 / 4; ++k4) {
+      const float4 w = wp[kW2Off0 / 4 + k4];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r][2 * k4 + 0] = ffma2(make_float2(w.x, w.y), h[r].x, acc[r][2 * k4 + 0]);
+        acc[r][2 * k4 + 1] = ffma2(make_float2(w.z, w.w), h[r].x, acc[r][2 * k4 + 1]);
+      }
+    }
+#pragma unroll
+    for (int k4 = 0; k4 < kH2 / 4; ++k4) {
+      const float4 w = wp[kW2Off1 / 4 + k4];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r][2 * k4 + 0] = ffma2(make_float2(w.x, w.y), h[r].y, acc[r][2 * k4 + 0]);
+        acc[r][2 * k4 + 1] = ffma2(make_float2(w.z, w.w), h[r].y, acc[r][2 * k4 + 1]);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float z = sm.w.b3;
+#pragma unroll
+    for (int k = 0; k < kH2 / 2; ++k) {
+      z = fmaf(sm.w.w3[2 * k], fmaxf(acc[r][k].x, 0.0f), z);
+      z = fmaf(sm.w.w3[2 * k + 1], fmaxf(acc[r][k].y, 0.0f), z);
+    }
+    const float p = 1.0f / (1.0f + expf(-z));
+    if (valid[r]) {
+      const int lr = cbase + r * kThreads + tid;
+      a.read_prob[r0 + lr] = p;
+      if (q_in_smem) sm.q[lr] = 1.0f - p;
+      if (p >= a.read_threshold) atomicAdd(&sm.cnt[site_l[r]], 1);
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 template <int NS>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -307,66 +376,14 @@ mil_infer_kernel(const KernelArgs a) {
       __syncthreads();  // feature buffer free again
       if (chunk + 1 < n_chunks) stage_chunk(chunk + 1);   // overlaps the MLP below
 
-      float2 acc[kReadsPerThread][kH2 / 2];
-#pragma unroll
-      for (int r = 0; r < kReadsPerThread; ++r)
-#pragma unroll
-        for (int k = 0; k < kH2 / 2; ++k) acc[r][k] = make_float2(sm.w.b2[2 * k], sm.w.b2[2 * k + 1]);
-
-#pragma unroll 1
-      for (int p = 0; p < n_pairs; ++p) {
-        const float4* wp = reinterpret_cast<const float4*>(sm.w.pair[p]);
-        const float4 u0 = wp[0], u1 = wp[1], u2 = wp[2], u3 = wp[3], u4 = wp[4];
-        float2 h[kReadsPerThread];
-#pragma unroll
-        for (int r = 0; r < kReadsPerThread; ++r) {
-          float2 t = *reinterpret_cast<const float2*>(cs[r] + 2 * p);
-          t = ffma2(make_float2(u0.x, u0.y), x[r][0], t);
-          t = ffma2(make_float2(u0.z, u0.w), x[r][1], t);
-          t = ffma2(make_float2(u1.x, u1.y), x[r][2], t);
-          t = ffma2(make_float2(u1.z, u1.w), x[r][3], t);
-          t = ffma2(make_float2(u2.x, u2.y), x[r][4], t);
-          t = ffma2(make_float2(u2.z, u2.w), x[r][5], t);
-          t = ffma2(make_float2(u3.x, u3.y), x[r][6], t);
-          t = ffma2(make_float2(u3.z, u3.w), x[r][7], t);
-          t = ffma2(make_float2(u4.x, u4.y), x[r][8], t);
-          h[r] = make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f));
-        }
-#pragma unroll
-        for (int k4 = 0; k4 < kH2 / 4; ++k4) {
-          const float4 w = wp[kW2Off0 / 4 + k4];
-#pragma unroll
-          for (int r = 0; r < kReadsPerThread; ++r) {
-            acc[r][2 * k4 + 0] = ffma2(make_float2(w.x, w.y), h[r].x, acc[r][2 * k4 + 0]);
-            acc[r][2 * k4 + 1] = ffma2(make_float2(w.z, w.w), h[r].x, acc[r][2 * k4 + 1]);
-          }
-        }
-#pragma unroll
-        for (int k4 = 0; k4 < kH2 / 4; ++k4) {
-          const float4 w = wp[kW2Off1 / 4 + k4];
-#pragma unroll
-          for (int r = 0; r < kReadsPerThread; ++r) {
-            acc[r][2 * k4 + 0] = ffma2(make_float2(w.x, w.y), h[r].y, acc[r][2 * k4 + 0]);
-            acc[r][2 * k4 + 1] = ffma2(make_float2(w.z, w.w), h[r].y, acc[r][2 * k4 + 1]);
-          }
-        }
-      }
-
-#pragma unroll
-      for (int r = 0; r < kReadsPerThread; ++r) {
-        float z = sm.w.b3;
-#pragma unroll
-        for (int k = 0; k < kH2 / 2; ++k) {
-          z = fmaf(sm.w.w3[2 * k], fmaxf(acc[r][k].x, 0.0f), z);
-          z = fmaf(sm.w.w3[2 * k + 1], fmaxf(acc[r][k].y, 0.0f), z);
-        }
-        const float p = 1.0f / (1.0f + expf(-z));
-        if (valid[r]) {
-          const int lr = cbase + r * kThreads + tid;
-          a.read_prob[r0 + lr] = p;
-          if (q_in_smem) sm.q[lr] = 1.0f - p;
-          if (p >= a.read_threshold) atomicAdd(&sm.cnt[site_l[r]], 1);
-        }
+      // Warp-uniform count of live read slots: ragged tiles leave the second slot (or both) of trailing warps empty,
+      // and those warps run the one-read instantiation (or nothing) instead of computing on clamped rows.
+      const bool any1 = __any_sync(0xffffffffu, valid[kReadsPerThread - 1]);
+      const bool any0 = __any_sync(0xffffffffu, valid[0]);
+      if (kReadsPerThread == 2 && any1) {
+        encode_reads<kReadsPerThread>(sm, a, x, cs, site_l, valid, r0, cbase, tid, n_pairs, q_in_smem);
+      } else if (any0) {
+        encode_reads<1>(sm, a, x, cs, site_l, valid, r0, cbase, tid, n_pairs, q_in_smem);
       }
     }
     __syncthreads();  // q, cnt and (fallback) read_prob of the whole tile are visible
