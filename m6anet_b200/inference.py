@@ -170,16 +170,66 @@ def run_inference(model: MILModel, dl, args):
     suffix = f".rank{rank}" if world > 1 else ""
     all_sp, all_mc = [], []
     eng = model.engine(dev)
-    with open(site_path + suffix, 'ab') as f, open(indiv_path + suffix, 'ab') as g:
-        for a, b in spans:
-            batch = ds.load_sites(a, b, n_threads=n_threads)                      # data.json -> flat buffers (native)
-            read_prob, site_prob, mod_count = eng.infer_host(batch.feats, batch.read_off, batch.kmer_idx, n_iters,
-                                                             seed=seed, site_id_base=a, n_samples=N_SAMPLES,
-                                                             read_threshold=thr)    # H2D -> kernel -> D2H
-            write_site_rows(f, batch, site_prob, mod_count, n_threads)
-            write_indiv_rows(g, batch, read_prob, n_threads)
+
+    # Three overlapped stages (the native calls release the GIL): ingest of batch i+1 | H2D/kernel/D2H of batch i |
+    # CSV emit of batch i-1.  Queues are bounded so at most ~3 batches are resident on the host.
+    import queue
+    import threading
+    q_in: "queue.Queue" = queue.Queue(maxsize=2)
+    q_out: "queue.Queue" = queue.Queue(maxsize=2)
+    errors: list = []
+
+    def ingest():
+        try:
+            for a, b in spans:
+                if errors:
+                    break
+                q_in.put((a, ds.load_sites(a, b, n_threads=n_threads)))        # data.json -> flat buffers (native)
+        except BaseException as e:   # noqa: BLE001 - re-raised in the main thread
+            errors.append(e)
+        finally:
+            q_in.put(None)
+
+    def emit():
+        try:
+            with open(site_path + suffix, 'ab') as f, open(indiv_path + suffix, 'ab') as g:
+                while True:
+                    item = q_out.get()
+                    if item is None:
+                        break
+                    batch, read_prob, site_prob, mod_count = item
+                    write_site_rows(f, batch, site_prob, mod_count, n_threads)
+                    write_indiv_rows(g, batch, read_prob, n_threads)
+        except BaseException as e:   # noqa: BLE001
+            errors.append(e)
+            while q_out.get() is not None:    # keep draining so the main thread never blocks on a full queue
+                pass
+
+    t_in = threading.Thread(target=ingest, name="m6a-ingest", daemon=True)
+    t_out = threading.Thread(target=emit, name="m6a-emit", daemon=True)
+    t_in.start()
+    t_out.start()
+    try:
+        while True:
+            item = q_in.get()
+            if item is None:
+                break
+            a, batch = item
+            if errors:
+                continue
+            with torch.cuda.device(dev):
+                read_prob, site_prob, mod_count = eng.infer_host(batch.feats, batch.read_off, batch.kmer_idx, n_iters,
+                                                                 seed=seed, site_id_base=a, n_samples=N_SAMPLES,
+                                                                 read_threshold=thr)    # H2D -> kernel -> D2H
             all_sp.append(site_prob)
             all_mc.append(mod_count)
+            q_out.put((batch, read_prob, site_prob, mod_count))
+    finally:
+        q_out.put(None)
+        t_in.join()
+        t_out.join()
+    if errors:
+        raise errors[0]
     site_prob = np.concatenate(all_sp) if all_sp else np.zeros(0, np.float32)
     mod_count = np.concatenate(all_mc) if all_mc else np.zeros(0, np.int32)
 
