@@ -215,6 +215,8 @@ def main():
     feats_h, off_h, kmer_h = synth_shard(sa, sb, a.reads, 1, a.ragged)
     thr = MODELS[a.model][1]
     eng = MilEngine(W.from_npz(os.path.join(ROOT, "m6anet_b200", "assets", "model_states", MODELS[a.model][0])), dev)
+    if a.ragged:
+        eng.set_tile_reads(1024)    # what the host path selects by itself for uneven read counts
 
     feats_p = torch.from_numpy(feats_h).pin_memory()
     off_p = torch.from_numpy(off_h).pin_memory()

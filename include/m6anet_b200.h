@@ -80,6 +80,9 @@ const char *m6a_strerror(int status);
  * device (synchronous).  The model may be used from any stream of that device. */
 int m6a_model_create(const m6a_weights_t *w, m6a_model_t **out);
 int m6a_model_destroy(m6a_model_t *model);
+/* Target feature rows per tile of the device call (default 512; 0 restores the default).  Sites with very
+ * uneven read counts are scored faster with ~1024; m6a_mil_infer_host_f32 chooses automatically. */
+int m6a_model_set_tile_reads(m6a_model_t *model, int32_t tile_reads);
 
 /*
  * Score n_sites sites.  All data pointers are DEVICE pointers.

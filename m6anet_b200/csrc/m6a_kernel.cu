@@ -39,7 +39,6 @@ struct Smem {
   int roff[kSitesPerTileMax + 1];
   int cnt[kSitesPerTileMax];
   int kid[kSitesPerTileMax][kKmerPos];
-  alignas(8) long long r0_next;          // first feature row of the CTA's next tile (header prefetch)
   alignas(8) unsigned long long bar_w;
   alignas(8) unsigned long long bar_f;
 };
@@ -146,13 +145,6 @@ __device__ __forceinline__ Span chunk_span(const KernelArgs& a, long long r0, in
   if (sp.g1 > gend) sp.g1 = gend;
   return sp;
 }
-// chunk 0 of a tile can be staged ahead of time iff one bulk copy covers it completely
-__device__ __forceinline__ bool chunk0_prefetchable(const KernelArgs& a, long long r0, int nr) {
-  if (!a.feats_tma_ok || nr <= 0) return false;
-  const Span sp = chunk_span(a, r0, nr, 0);
-  return sp.g1 > sp.g0 && sp.b1 <= sp.g1;
-}
-
 // ---- read encoder for R reads per thread (R = 2 full chunk rows, R = 1 for a warp whose second slot is empty) --
 template <int R>
 __device__ __forceinline__ void encode_reads(Smem& sm, const KernelArgs& a, const float (&x)[kReadsPerThread][kNSig],
@@ -251,42 +243,26 @@ mil_infer_kernel(const KernelArgs a) {
   const bool tma_ok = a.feats_tma_ok;
   const float n_iters_f = static_cast<float>(a.n_iters);
 
-  // header prefetch state (registers): this thread's CSR offset and k-mer ids of the CTA's NEXT tile
-  bool pf_valid = false;
-  long long pf_off = 0;
-  int pf_kid[kKmerPos] = {0, 0, 0};
-
   for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const long long s0 = tile * a.sites_per_tile;
     const int ns = static_cast<int>(min(static_cast<long long>(a.sites_per_tile), a.n_sites - s0));
+    const long long r0 = a.read_off[s0];
 
     // ---- tile header: local CSR offsets, k-mer ids, counters ------------------------------------
-    // (prefetched during the previous tile's phase B; plain global loads for the CTA's first tile)
-    long long my_off = pf_off;
-    int my_kid[kKmerPos] = {pf_kid[0], pf_kid[1], pf_kid[2]};
-    long long r0;
-    if (pf_valid) {
-      r0 = sm.r0_next;                         // written by thread 0 before the previous tile's closing barrier
-    } else {
-      r0 = a.read_off[s0];
-      if (tid <= ns) my_off = a.read_off[s0 + tid];
-      if (tid < ns && a.kmer_idx != nullptr) {
-#pragma unroll
-        for (int t = 0; t < kKmerPos; ++t) my_kid[t] = a.kmer_idx[(s0 + tid) * kKmerPos + t];
-      }
-    }
-    if (tid <= ns) sm.roff[tid] = static_cast<int>(my_off - r0);
+    if (tid <= ns) sm.roff[tid] = static_cast<int>(a.read_off[s0 + tid] - r0);
     if (tid < ns) {
       sm.cnt[tid] = 0;
 #pragma unroll
-      for (int t = 0; t < kKmerPos; ++t)
-        sm.kid[tid][t] = (a.model.n_kmer == 1 || a.kmer_idx == nullptr) ? 0 : min(max(my_kid[t], 0), a.model.n_kmer - 1);
+      for (int t = 0; t < kKmerPos; ++t) {
+        int k = a.kmer_idx != nullptr ? a.kmer_idx[(s0 + tid) * kKmerPos + t] : 0;
+        k = (a.model.n_kmer == 1) ? 0 : min(max(k, 0), a.model.n_kmer - 1);
+        sm.kid[tid][t] = k;
+      }
     }
     __syncthreads();
     const int nr = sm.roff[ns];                 // reads in this tile
     const bool q_in_smem = nr <= kQCap;
     const int n_chunks = (nr + kChunkReads - 1) / kChunkReads;
-    const bool chunk0_staged = pf_valid && chunk0_prefetchable(a, r0, nr);   // same predicate thread 0 used when it issued it
 
     // ---- feature staging: rows [ra, ra+rows) of feats -> sm.feat[head + i*9 + k] ---------------------
     auto stage_chunk = [&](int chunk) {
@@ -310,7 +286,7 @@ mil_infer_kernel(const KernelArgs a) {
       }
     };
 
-    if (n_chunks > 0 && !chunk0_staged) stage_chunk(0);
+    if (n_chunks > 0) stage_chunk(0);
 
     // c_site[s][j] = ctab0[k0][j] + ctab1[k1][j] + ctab2[k2][j]   (coalesced over j, L2 resident).
     // Four elements per thread per batch, all 12 loads issued before the first add: one L2 round trip per batch.
@@ -388,22 +364,6 @@ mil_infer_kernel(const KernelArgs a) {
     }
     __syncthreads();  // q, cnt and (fallback) read_prob of the whole tile are visible
 
-    // ---- prefetch the header of this CTA's next tile: the loads fly during phase B ---------------------------
-    const long long tile_n = tile + gridDim.x;
-    const bool has_next = (M6A_PREFETCH != 0) && tile_n < a.n_tiles;
-    long long pf_end = 0;                         // thread 0: one past the last feature row of the next tile
-    if (has_next) {
-      const long long s0n = tile_n * a.sites_per_tile;
-      const int nsn = static_cast<int>(min(static_cast<long long>(a.sites_per_tile), a.n_sites - s0n));
-      if (tid <= nsn) pf_off = a.read_off[s0n + tid];
-      if (tid < nsn && a.kmer_idx != nullptr) {
-#pragma unroll
-        for (int t = 0; t < kKmerPos; ++t) pf_kid[t] = a.kmer_idx[(s0n + tid) * kKmerPos + t];
-      }
-      if (tid == 0) pf_end = a.read_off[s0n + nsn];
-    }
-    pf_valid = has_next;
-
     // ---- phase B: Monte-Carlo noisy-OR ----------------------------------------------------------
     {
       // items (site, block) are dealt round-robin to the warps; (sl, blk) advance without a division
@@ -436,18 +396,6 @@ mil_infer_kernel(const KernelArgs a) {
         if (lane == 0) sm.partial[sl][blk] = v;
         blk += kWarps;
         while (blk >= n_blocks) { blk -= n_blocks; ++sl; }
-      }
-    }
-    // The feature buffer is idle since the last chunk went to registers: stage the next tile's first chunk now,
-    // so that the copy overlaps the barriers, the finalize step and the next c_site gather.
-    if (tid == 0 && has_next) {
-      sm.r0_next = pf_off;
-      const int nrn = static_cast<int>(pf_end - pf_off);
-      if (chunk0_prefetchable(a, pf_off, nrn)) {
-        const Span sp = chunk_span(a, pf_off, nrn, 0);
-        mbar_expect_tx(&sm.bar_f, static_cast<uint32_t>(sp.g1 - sp.g0));
-        bulk_g2s(sm.feat, reinterpret_cast<const unsigned char*>(a.feats) + sp.g0, static_cast<uint32_t>(sp.g1 - sp.g0),
-                 &sm.bar_f);
       }
     }
     __syncthreads();

@@ -24,10 +24,6 @@ namespace m6a {
 #ifndef M6A_QCAP
 #define M6A_QCAP 4096
 #endif
-#ifndef M6A_PREFETCH
-#define M6A_PREFETCH 0      // prefetch the next tile's header + first feature chunk during phase B.  Measured on B200
-                            // (1M x 50 x 1000): 21.86 ms with, 21.36 ms without -> off (kept for re-evaluation on ragged data)
-#endif
 #ifndef M6A_TILE_READS
 #define M6A_TILE_READS (M6A_THREADS * M6A_RPT)
 #endif

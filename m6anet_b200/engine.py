@@ -44,6 +44,10 @@ class MilEngine:
             _cabi.check(self._lib.m6a_model_create(C.byref(w), C.byref(handle)), "m6a_model_create")
         self._handle = handle
 
+    def set_tile_reads(self, tile_reads: int = 0):
+        """Target feature rows per tile of infer_device (0 = default 512; ~1024 suits very uneven read counts)."""
+        _cabi.check(self._lib.m6a_model_set_tile_reads(self._handle, int(tile_reads)), "m6a_model_set_tile_reads")
+
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle.value:
             self._lib.m6a_model_destroy(self._handle)
