@@ -151,11 +151,11 @@ static int sites_per_tile_for(long long n_sites, long long total_reads, int tile
   return static_cast<int>(std::min<long long>(kSitesPerTileMax, std::max<long long>(1, g)));
 }
 
-extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, const int64_t* read_off,
-                                 const int32_t* kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
-                                 int32_t n_samples, int32_t n_iters, uint64_t seed, const uint16_t* sample_idx,
-                                 float read_threshold, float* read_prob, float* site_prob, int32_t* mod_count,
-                                 void* stream) {
+static int infer_device_impl(const m6a_model_t* model, int tile_reads, const float* feats, const int64_t* read_off,
+                             const int32_t* kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
+                             int32_t n_samples, int32_t n_iters, uint64_t seed, const uint16_t* sample_idx,
+                             float read_threshold, float* read_prob, float* site_prob, int32_t* mod_count,
+                             void* stream) {
   if (!model || n_sites < 0 || total_reads < 0) return M6A_EINVAL;
   if (n_samples < 1 || n_samples > 64 || n_iters < 1) return M6A_EINVAL;
   if (n_sites == 0) return M6A_OK;
@@ -175,7 +175,7 @@ extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, c
   a.site_prob = site_prob;
   a.mod_count = mod_count;
   a.n_sites = n_sites;
-  a.sites_per_tile = sites_per_tile_for(n_sites, total_reads, model->tile_reads);
+  a.sites_per_tile = sites_per_tile_for(n_sites, total_reads, tile_reads);
   a.n_tiles = (n_sites + a.sites_per_tile - 1) / a.sites_per_tile;
   a.site_id_base = site_id_base;
   a.feats_bytes = static_cast<unsigned long long>(total_reads) * (kNSig * sizeof(float));
@@ -192,6 +192,16 @@ extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, c
   g_last = info;
   g_last_launches = 1;
   return M6A_OK;
+}
+
+extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, const int64_t* read_off,
+                                 const int32_t* kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
+                                 int32_t n_samples, int32_t n_iters, uint64_t seed, const uint16_t* sample_idx,
+                                 float read_threshold, float* read_prob, float* site_prob, int32_t* mod_count,
+                                 void* stream) {
+  if (!model) return M6A_EINVAL;
+  return infer_device_impl(model, model->tile_reads, feats, read_off, kmer_idx, n_sites, total_reads, site_id_base, n_samples,
+                           n_iters, seed, sample_idx, read_threshold, read_prob, site_prob, mod_count, stream);
 }
 
 extern "C" int m6a_sample_indices(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters, int32_t n_samples,
@@ -300,18 +310,13 @@ extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model_c, const float* f
   std::lock_guard<std::mutex> guard(model->ws_mutex);
   // Ragged sites (real data: 20..1000+ reads) are scored ~5% faster with tiles of ~1024 rows, constant-depth
   // sites ~1% faster with ~512 (profiles/r01_tile_size_ab.txt); the host path sees read_off and picks.
-  const int saved_tile_reads = model->tile_reads;
-  if (saved_tile_reads == kTileReads) {
+  int tile_reads = model->tile_reads;
+  if (tile_reads == kTileReads) {
     int64_t max_n = 0;
     for (int64_t i = 0; i < n_sites; ++i) max_n = std::max(max_n, read_off[i + 1] - read_off[i]);
     const double mean_n = static_cast<double>(total_reads) / static_cast<double>(n_sites);
-    if (static_cast<double>(max_n) > 1.25 * mean_n + 1.0) model->tile_reads = std::min(1024, kQCap);
+    if (static_cast<double>(max_n) > 1.25 * mean_n + 1.0) tile_reads = std::min(1024, kQCap);
   }
-  struct Restore {
-    m6a_model* m;
-    int v;
-    ~Restore() { m->tile_reads = v; }
-  } restore{model, saved_tile_reads};
   const int n_slots = std::min(kHostSlots, n_chunks);
   for (int s = 0; s < n_slots; ++s) M6A_CUDA(slot_reserve(model->slots[s], max_sites, std::max<int64_t>(1, max_reads)));
 
@@ -336,7 +341,7 @@ extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model_c, const float* f
       rc = static_cast<int>(e);
       break;
     }
-    rc = m6a_mil_infer_f32(model, static_cast<const float*>(sl.d_feats), static_cast<const int64_t*>(sl.d_off),
+    rc = infer_device_impl(model, tile_reads, static_cast<const float*>(sl.d_feats), static_cast<const int64_t*>(sl.d_off),
                            kmer_idx ? static_cast<const int32_t*>(sl.d_kmer) : nullptr, ns, nr, site_id_base + sa,
                            n_samples, n_iters, seed, nullptr, read_threshold, static_cast<float*>(sl.d_rp),
                            static_cast<float*>(sl.d_sp), static_cast<int32_t*>(sl.d_mc), sl.stream);
