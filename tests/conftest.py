@@ -38,6 +38,15 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The suites need the in-tree C-ABI library (nvcc cross-compiles without a GPU); build it once if absent."""
+    from m6anet_b200 import _cabi
+    if not os.path.exists(_cabi.LIB_PATH):
+        _cabi.build()
+    return _cabi.LIB_PATH
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

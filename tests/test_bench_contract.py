@@ -1,0 +1,52 @@
+"""bench.py contract: one JSON line on stdout with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"}
+
+
+def run_bench(*args, timeout=900):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=timeout,
+                       cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout          # exactly ONE line on stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--sites", "3000", "--cpu-sample-sites", "3000")
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["metric"] == "DRACH sites/sec at num_iterations=1000" and d["unit"] == "sites/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_b200_arm_line():
+    d = run_bench("--steps", "3", "--warmup", "3", "--sites", "60000", "--cpu-sample-sites", "2000")
+    assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"] == "fp32" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert d["value"] > 1e6 and d["gpu_launches"] == 3
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert rf["algorithmic_bytes_per_launch"] == 60000 * 2028
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 60000 * 50 * 36 and e["d2h_bytes_per_step"] > 60000 * 50 * 4
+    assert e["matches_resident_path"] is True
+    assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
