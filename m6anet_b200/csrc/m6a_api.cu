@@ -24,6 +24,7 @@ struct HostSlot {   // one stage of the host-buffer pipeline (m6a_mil_infer_host
 
 struct m6a_model {
   DeviceModel dev;
+  WeightImage host_image;        // packed weights, host copy (kernel-parameter path)
   void* d_image;
   void* d_ctab;
   int device;
@@ -112,6 +113,7 @@ extern "C" int m6a_model_create(const m6a_weights_t* w, m6a_model_t** out) {
   if (e == cudaSuccess) e = cudaMalloc(&m->d_ctab, ctab.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(m->d_image, img, sizeof(WeightImage), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(m->d_ctab, ctab.data(), ctab.size() * sizeof(float), cudaMemcpyHostToDevice);
+  m->host_image = *img;
   free(img);
   if (e != cudaSuccess) {
     if (m->d_image) cudaFree(m->d_image);
@@ -187,7 +189,7 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
   a.feats_tma_ok = (reinterpret_cast<uintptr_t>(feats) & 15u) == 0;
 
   LaunchInfo info;
-  cudaError_t e = launch_mil_infer(a, model->n_sms, static_cast<cudaStream_t>(stream), &info);
+  cudaError_t e = launch_mil_infer(a, &model->host_image, model->n_sms, static_cast<cudaStream_t>(stream), &info);
   if (e != cudaSuccess) return static_cast<int>(e);
   g_last = info;
   g_last_launches = 1;

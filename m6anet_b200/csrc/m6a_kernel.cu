@@ -31,7 +31,9 @@
 namespace m6a {
 
 struct Smem {
-  WeightImage w;
+#if !M6A_WEIGHTS_CONST
+  WeightImage w;                                    // staged once per CTA by one bulk copy
+#endif
   alignas(16) float feat[kChunkReads * kNSig + 8];  // + unaligned head (<=3 floats) + tail round-up
   alignas(16) float csite[kSitesPerTileMax][kCStride];
   float q[kQCap];
@@ -100,14 +102,33 @@ template <int NS>
 __device__ __forceinline__ float mc_lane_smem(const float* __restrict__ qs, uint32_t n, Mwc64x& g, int rounds) {
   const uint32_t qaddr = smem_u32(qs);     // shared-space byte address of the site's q table
   float v = 0.0f;
-  for (int k = 0; k < rounds; ++k) {
-    float prod = 1.0f;
+  if (n <= kPairedMaxReads) {              // warp-uniform: two indices per word
+    for (int k = 0; k < rounds; ++k) {
+      float prod = 1.0f;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const uint32_t idx = __umulhi(g.next(), n);
-      prod *= lds_f32(qaddr + (idx << 2));   // IMAD.HI, LEA, LDS, FMUL
+      for (int s = 0; s < NS / 2; ++s) {
+        uint32_t i1, i2;
+        g.next_pair(n, i1, i2);
+        prod *= lds_f32(qaddr + (i1 << 2));  // IMAD.WIDE, IMAD.HI, 2 x (LEA, LDS, FMUL) per word
+        prod *= lds_f32(qaddr + (i2 << 2));
+      }
+      if (NS & 1) {
+        uint32_t i1, i2;
+        g.next_pair(n, i1, i2);
+        prod *= lds_f32(qaddr + (i1 << 2));
+      }
+      v += 1.0f - prod;
     }
-    v += 1.0f - prod;
+  } else {
+    for (int k = 0; k < rounds; ++k) {
+      float prod = 1.0f;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const uint32_t idx = __umulhi(g.next(), n);
+        prod *= lds_f32(qaddr + (idx << 2));   // IMAD.HI, LEA, LDS, FMUL
+      }
+      v += 1.0f - prod;
+    }
   }
   return v;
 }
@@ -117,10 +138,21 @@ __device__ __forceinline__ float mc_lane_generic(const float* qbase, bool from_p
                                                  int ns, const uint16_t* __restrict__ explicit_idx,
                                                  size_t explicit_round_stride) {
   float v = 0.0f;
+  const bool paired = n <= kPairedMaxReads;
   for (int k = 0; k < rounds; ++k) {
     float prod = 1.0f;
+    uint32_t pending = 0;
     for (int s = 0; s < ns; ++s) {
-      const uint32_t i = explicit_idx != nullptr ? explicit_idx[k * explicit_round_stride + s] : __umulhi(g.next(), n);
+      uint32_t i;
+      if (explicit_idx != nullptr) {
+        i = explicit_idx[k * explicit_round_stride + s];
+      } else if (!paired) {
+        i = __umulhi(g.next(), n);
+      } else if ((s & 1) == 0) {
+        g.next_pair(n, i, pending);
+      } else {
+        i = pending;
+      }
       prod *= from_prob ? 1.0f - qbase[i] : qbase[i];
     }
     v += 1.0f - prod;
@@ -147,7 +179,8 @@ __device__ __forceinline__ Span chunk_span(const KernelArgs& a, long long r0, in
 }
 // ---- read encoder for R reads per thread (R = 2 full chunk rows, R = 1 for a warp whose second slot is empty) --
 template <int R>
-__device__ __forceinline__ void encode_reads(Smem& sm, const KernelArgs& a, const float (&x)[kReadsPerThread][kNSig],
+__device__ __forceinline__ void encode_reads(Smem& sm, const WeightImage& W, const KernelArgs& a,
+                                             const float (&x)[kReadsPerThread][kNSig],
                                              const float* const (&cs)[kReadsPerThread], const int (&site_l)[kReadsPerThread],
                                              const bool (&valid)[kReadsPerThread], long long r0, int cbase, int tid,
                                              int n_pairs, bool q_in_smem) {
@@ -155,11 +188,11 @@ __device__ __forceinline__ void encode_reads(Smem& sm, const KernelArgs& a, cons
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int k = 0; k < kH2 / 2; ++k) acc[r][k] = make_float2(sm.w.b2[2 * k], sm.w.b2[2 * k + 1]);
+    for (int k = 0; k < kH2 / 2; ++k) acc[r][k] = make_float2(W.b2[2 * k], W.b2[2 * k + 1]);
 
-#pragma unroll 1
+#pragma unroll kPairUnroll
   for (int p = 0; p < n_pairs; ++p) {
-    const float4* wp = reinterpret_cast<const float4*>(sm.w.pair[p]);
+    const float4* wp = reinterpret_cast<const float4*>(W.pair[p]);
     const float4 u0 = wp[0], u1 = wp[1], u2 = wp[2], u3 = wp[3], u4 = wp[4];
     float2 h[R];
 #pragma unroll
@@ -198,11 +231,11 @@ __device__ __forceinline__ void encode_reads(Smem& sm, const KernelArgs& a, cons
 
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    float z = sm.w.b3;
+    float z = W.b3;
 #pragma unroll
     for (int k = 0; k < kH2 / 2; ++k) {
-      z = fmaf(sm.w.w3[2 * k], fmaxf(acc[r][k].x, 0.0f), z);
-      z = fmaf(sm.w.w3[2 * k + 1], fmaxf(acc[r][k].y, 0.0f), z);
+      z = fmaf(W.w3[2 * k], fmaxf(acc[r][k].x, 0.0f), z);
+      z = fmaf(W.w3[2 * k + 1], fmaxf(acc[r][k].y, 0.0f), z);
     }
     const float p = 1.0f / (1.0f + expf(-z));
     if (valid[r]) {
@@ -217,9 +250,21 @@ __device__ __forceinline__ void encode_reads(Smem& sm, const KernelArgs& a, cons
 // -------------------------------------------------------------------------------------------------
 template <int NS>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
+#if M6A_WEIGHTS_CONST
+mil_infer_kernel(const KernelArgs a, const __grid_constant__ WeightImage wparam) {
+#else
 mil_infer_kernel(const KernelArgs a) {
+#endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+#if M6A_WEIGHTS_CONST
+  // The weights are a kernel parameter (constant bank 0): ptxas feeds them to FFMA2 through uniform registers
+  // (LDCU.64 UR, c[0x0][UR+imm]; FFMA2 R, R.F32, UR.F32x2, R), so they use neither shared-memory bandwidth nor
+  // vector registers.
+  const WeightImage& W = wparam;
+#else
+  const WeightImage& W = sm.w;
+#endif
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -231,12 +276,16 @@ mil_infer_kernel(const KernelArgs a) {
     fence_barrier_init();
   }
   __syncthreads();
+#if M6A_WEIGHTS_CONST
+  bool weights_ready = true;
+#else
   if (tid == 0) {
     mbar_expect_tx(&sm.bar_w, static_cast<uint32_t>(sizeof(WeightImage)));
     bulk_g2s(&sm.w, a.model.image, static_cast<uint32_t>(sizeof(WeightImage)), &sm.bar_w);
   }
-  uint32_t f_parity = 0;
   bool weights_ready = false;
+#endif
+  uint32_t f_parity = 0;
 
   const int n_pairs = (a.model.h1 + 1) >> 1;
   const int n_blocks = a.n_blocks, ipl = a.iters_per_lane;
@@ -357,9 +406,9 @@ mil_infer_kernel(const KernelArgs a) {
       const bool any1 = __any_sync(0xffffffffu, valid[kReadsPerThread - 1]);
       const bool any0 = __any_sync(0xffffffffu, valid[0]);
       if (kReadsPerThread == 2 && any1) {
-        encode_reads<kReadsPerThread>(sm, a, x, cs, site_l, valid, r0, cbase, tid, n_pairs, q_in_smem);
+        encode_reads<kReadsPerThread>(sm, W, a, x, cs, site_l, valid, r0, cbase, tid, n_pairs, q_in_smem);
       } else if (any0) {
-        encode_reads<1>(sm, a, x, cs, site_l, valid, r0, cbase, tid, n_pairs, q_in_smem);
+        encode_reads<1>(sm, W, a, x, cs, site_l, valid, r0, cbase, tid, n_pairs, q_in_smem);
       }
     }
     __syncthreads();  // q, cnt and (fallback) read_prob of the whole tile are visible
@@ -425,14 +474,22 @@ __global__ void sample_indices_kernel(uint64_t seed, uint64_t site_id, uint32_t 
   for (int k = 0; k < ipl; ++k) {
     const long long it = (static_cast<long long>(blk) * ipl + k) * 32 + lane;
     if (it >= n_iters) break;
-    for (int s = 0; s < n_samples; ++s) out[it * n_samples + s] = static_cast<int32_t>(__umulhi(g.next(), n_reads));
+    uint32_t pending = 0;
+    for (int s = 0; s < n_samples; ++s) {
+      uint32_t i;
+      if (n_reads > kPairedMaxReads) i = __umulhi(g.next(), n_reads);
+      else if ((s & 1) == 0) g.next_pair(n_reads, i, pending);
+      else i = pending;
+      out[it * n_samples + s] = static_cast<int32_t>(i);
+    }
   }
 }
 
 // ---- host-side launchers ---------------------------------------------------------------------------
 static int g_max_ctas_per_sm[2] = {-1, -1};
 
-cudaError_t launch_mil_infer(const KernelArgs& a, int n_sms, cudaStream_t stream, LaunchInfo* info) {
+cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image, int n_sms, cudaStream_t stream,
+                             LaunchInfo* info) {
   const bool fast = (a.n_samples == 20);
   auto kfast = mil_infer_kernel<20>;
   auto kgen = mil_infer_kernel<0>;
@@ -457,10 +514,18 @@ cudaError_t launch_mil_infer(const KernelArgs& a, int n_sms, cudaStream_t stream
     info->smem_bytes = smem;
     info->sites_per_tile = a.sites_per_tile;
   }
+#if M6A_WEIGHTS_CONST
+  if (fast)
+    kfast<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a, *host_image);
+  else
+    kgen<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a, *host_image);
+#else
+  (void)host_image;
   if (fast)
     kfast<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a);
   else
     kgen<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a);
+#endif
   return cudaGetLastError();
 }
 

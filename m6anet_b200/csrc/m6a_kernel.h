@@ -24,9 +24,16 @@ namespace m6a {
 #ifndef M6A_QCAP
 #define M6A_QCAP 4096
 #endif
+#ifndef M6A_WEIGHTS_CONST
+#define M6A_WEIGHTS_CONST 1   // 1: weight image as a __grid_constant__ kernel parameter (uniform datapath) instead of shared memory
+#endif
+#ifndef M6A_PAIR_UNROLL
+#define M6A_PAIR_UNROLL 5   // pair-loop unroll: deeper LDCU lookahead (1: 19.4 ms, 3: 18.36, 5: 18.35, 15: 17.8 but ragged 24.7)
+#endif
 #ifndef M6A_TILE_READS
 #define M6A_TILE_READS (M6A_THREADS * M6A_RPT)
 #endif
+constexpr int kPairUnroll = M6A_PAIR_UNROLL;
 constexpr int kThreads = M6A_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kReadsPerThread = M6A_RPT;
@@ -75,7 +82,8 @@ struct LaunchInfo {
 };
 
 size_t smem_bytes();
-cudaError_t launch_mil_infer(const KernelArgs& a, int n_sms, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image, int n_sms, cudaStream_t stream,
+                             LaunchInfo* info);
 cudaError_t launch_sample_indices(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
                                   int32_t* out, cudaStream_t stream);
 

@@ -13,8 +13,11 @@ constexpr int kPairFloats = 84;    // per pair p=(j0,j1): 9 x (w1[j0,k], w1[j1,k
 constexpr int kW2Off0 = 20;        // float offset of w2[:, j0]
 constexpr int kW2Off1 = 52;        // float offset of w2[:, j1]
 
-// Image of the read-encoder weights as the kernel wants them in shared memory.  One
-// cp.async.bulk moves it.  Hidden units go in pairs (j0, j1) = (2p, 2p+1): the 9 signal weights of
+// Image of the read-encoder weights as the kernel consumes them.  It is passed BY VALUE as a __grid_constant__
+// kernel parameter (constant bank 0, 25.9 KB of the 32 KB limit): ptxas then streams it through the uniform
+// datapath (LDCU.64 UR, c[0x0][UR+imm]) and FFMA2 takes the pair as a uniform-register operand, so the weights
+// use neither shared-memory bandwidth nor vector registers (with -DM6A_WEIGHTS_CONST=0 the same image is staged in
+// shared memory by one cp.async.bulk instead: 7 % slower, profiles/r01_tile_size_ab.txt).  Hidden units go in pairs (j0, j1) = (2p, 2p+1): the 9 signal weights of
 // Linear-1 (BatchNorm folded) are interleaved as float2 (w1[j0,k], w1[j1,k]) so that one FFMA2 with
 // the scalar x_k updates (h_j0, h_j1); columns j0 and j1 of Linear-2 follow as 2 x 16 float2 so that
 // one FFMA2 with the scalar h_j updates two outputs.  The pair loop reads 21 consecutive float4 at a

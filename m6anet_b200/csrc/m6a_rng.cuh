@@ -5,7 +5,10 @@
 //   seeding   (w0, w1, _, _) = Philox4x32-10(ctr = (lane, block, site_lo, site_hi), key = (seed_lo, seed_hi))
 //             x = w0;  c = (w1 * (A-1)) >> 32;  if (x == 0 && c == 0) x = 1
 //   draw      word = x ^ c;  (c:x) = A * x + c                       A = 4294883355 (MWC64X, D. B. Thomas)
-//   index     (word * n_reads) >> 32
+//   index     n_reads >  256: one index per word,  (word * n_reads) >> 32                     (bias <= n / 2^32)
+//             n_reads <= 256: two indices per word, t = word * n_reads (64 bit):  i1 = t >> 32,
+//                             i2 = ((t & 0xffffffff) * n_reads) >> 32                         (bias <= n^2 / 2^32 <= 1.6e-5)
+//             an iteration consumes ceil(n_samples / 2) words in the paired regime (an odd last half is dropped)
 //
 // Why not Philox per draw: on sm_100a IMAD.WIDE/IMAD.HI issue at a quarter of the FFMA rate and
 // occupy the FMA pipe (tools/microbench/rates.cu); Philox4x32-10 needs 20 of them per 4 words, the
@@ -21,6 +24,7 @@ constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
 constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 constexpr uint32_t kMwcA = 4294883355u;
 constexpr int kMaxBlocks = 64;          // MC partial sums per site
+constexpr uint32_t kPairedMaxReads = 256;   // sites with at most this many reads draw two indices per word
 constexpr int kMinItersPerLane = 8;
 
 struct Philox4 {
@@ -66,6 +70,13 @@ struct Mwc64x {
     x = nx;
     c = nc;
     return word;
+  }
+  // two indices from one word (paired regime): the wide product's high half is the first index, its low half is a
+  // fresh uniform word for the second
+  __device__ __forceinline__ void next_pair(uint32_t n, uint32_t& i1, uint32_t& i2) {
+    const uint64_t t = static_cast<uint64_t>(next()) * n;
+    i1 = static_cast<uint32_t>(t >> 32);
+    i2 = __umulhi(static_cast<uint32_t>(t), n);
   }
 };
 

@@ -49,11 +49,14 @@ void oracle_sample_indices(uint64_t seed, uint64_t site_id, uint32_t n_reads, in
       for (int k = 0; k < ipl; ++k) {
         const long long it = ((long long)b * ipl + k) * 32 + l;
         if (it >= n_iters) break;
-        for (int s = 0; s < n_samples; ++s) {
+        for (int s = 0; s < n_samples;) {
           const uint32_t word = x ^ cy;
           const uint64_t t = (uint64_t)MWC_A * x + cy;
           x = (uint32_t)t; cy = (uint32_t)(t >> 32);
-          out[it * n_samples + s] = (int32_t)(((uint64_t)word * n_reads) >> 32);
+          const uint64_t u = (uint64_t)word * n_reads;
+          out[it * n_samples + s++] = (int32_t)(u >> 32);
+          if (n_reads <= 256u && s < n_samples)        /* paired regime: the low half is a second uniform word */
+            out[it * n_samples + s++] = (int32_t)(((u & 0xffffffffu) * n_reads) >> 32);
         }
       }
     }

@@ -24,7 +24,12 @@ Every (site, block, lane) owns an independent generator:
                                            key = (seed & 0xffffffff, seed >> 32))
             x = w0;  c = (w1 * (A - 1)) >> 32;  if x == c == 0: x = 1          (A = 4294883355)
   draw      word = x ^ c;  t = A * x + c (64 bit);  x = t & 0xffffffff;  c = t >> 32     (MWC64X, D. B. Thomas 2011)
-  index     (word * n_reads) >> 32                                   (bias <= n_reads / 2**32)
+  index     n_reads >  256: one index per word:   (word * n_reads) >> 32               (bias <= n_reads / 2**32)
+            n_reads <= 256: two indices per word: u = word * n_reads (64 bit);  i1 = u >> 32;
+                            i2 = ((u & 0xffffffff) * n_reads) >> 32                    (bias <= n_reads**2 / 2**32 <= 1.6e-5)
+            (the low half of the first product is again uniform on a lattice of spacing n_reads; the paired regime
+             halves the generator steps and the quarter-rate high multiplies on the device).  An iteration consumes
+             ceil(n_samples / 2) words in the paired regime; an unused odd half is dropped.
 
 and draws, in order, the ``n_samples`` indices of its round 0, then round 1, ... .  Philox4x32-10
 (Salmon et al., SC'11; the cuRAND / PyTorch-CUDA generator) gives key/counter separation, so a
@@ -44,6 +49,7 @@ _MASK32 = np.uint64(0xFFFFFFFF)
 _SHIFT32 = np.uint64(32)
 MAX_BLOCKS = 64
 MIN_ITERS_PER_LANE = 8
+PAIRED_MAX_READS = 256
 
 
 def philox4x32_10(ctr, key):
@@ -83,13 +89,9 @@ def block_layout(n_iters: int):
     return ipl, -(-int(n_iters) // (32 * ipl))
 
 
-def sample_indices_many(seed: int, site_ids, n_reads, n_iters: int, n_samples: int = 20) -> np.ndarray:
-    """Device index stream for several sites -> int64 [n_sites, n_iters, n_samples]."""
-    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    site_ids = np.asarray(site_ids, dtype=np.uint64).reshape(-1)
-    n_reads = np.asarray(n_reads, dtype=np.uint64).reshape(-1)
+def _streams(seed: int, site_ids: np.ndarray, n_blocks: int):
+    """Philox-seeded MWC64X states (x, c), uint64 arrays [S, n_blocks, 32]."""
     S = len(site_ids)
-    ipl, n_blocks = block_layout(n_iters)
     ctr = np.empty((S, n_blocks, 32, 4), dtype=np.uint32)
     ctr[..., 0] = np.arange(32, dtype=np.uint32)[None, None, :]
     ctr[..., 1] = np.arange(n_blocks, dtype=np.uint32)[None, :, None]
@@ -100,17 +102,44 @@ def sample_indices_many(seed: int, site_ids, n_reads, n_iters: int, n_samples: i
     x = w[..., 0].astype(np.uint64)
     c = (w[..., 1].astype(np.uint64) * np.uint64(MWC_A - 1)) >> _SHIFT32
     x = np.where((x == 0) & (c == 0), np.uint64(1), x)
+    return x, c
+
+
+def _draw_group(seed, site_ids, n_reads, n_iters, n_samples, paired: bool) -> np.ndarray:
+    """All sites of one regime (single / paired) -> int64 [S, n_iters, n_samples]."""
+    S = len(site_ids)
+    ipl, n_blocks = block_layout(n_iters)
+    x, c = _streams(seed, site_ids, n_blocks)
     A = np.uint64(MWC_A)
-    # out laid out [S, block, round, lane, sample] == iteration-major after reshape
-    out = np.empty((S, n_blocks, ipl, 32, n_samples), dtype=np.int64)
+    out = np.empty((S, n_blocks, ipl, 32, n_samples), dtype=np.int64)   # [S, block, round, lane, sample]
     nr = n_reads[:, None, None]
     for k in range(ipl):
-        for s in range(n_samples):
+        s = 0
+        while s < n_samples:
             word = x ^ c
-            out[:, :, k, :, s] = ((word * nr) >> _SHIFT32).astype(np.int64)
             t = A * x + c
             x, c = t & _MASK32, t >> _SHIFT32
+            u = word * nr                                   # < 2**64
+            out[:, :, k, :, s] = (u >> _SHIFT32).astype(np.int64)
+            s += 1
+            if paired and s < n_samples:
+                out[:, :, k, :, s] = (((u & _MASK32) * nr) >> _SHIFT32).astype(np.int64)
+                s += 1
     return out.reshape(S, n_blocks * ipl * 32, n_samples)[:, :n_iters, :]
+
+
+def sample_indices_many(seed: int, site_ids, n_reads, n_iters: int, n_samples: int = 20) -> np.ndarray:
+    """Device index stream for several sites -> int64 [n_sites, n_iters, n_samples]."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    site_ids = np.asarray(site_ids, dtype=np.uint64).reshape(-1)
+    n_reads = np.asarray(n_reads, dtype=np.uint64).reshape(-1)
+    out = np.empty((len(site_ids), n_iters, n_samples), dtype=np.int64)
+    paired = n_reads <= PAIRED_MAX_READS
+    for flag in (False, True):
+        sel = np.nonzero(paired == flag)[0]
+        if len(sel):
+            out[sel] = _draw_group(seed, site_ids[sel], n_reads[sel], n_iters, n_samples, flag)
+    return out
 
 
 def sample_indices(seed: int, site_id: int, n_reads: int, n_iters: int, n_samples: int = 20) -> np.ndarray:

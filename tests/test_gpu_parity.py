@@ -67,11 +67,13 @@ def test_library_is_loaded_and_native():
         assert "libm6anet_b200.so" in f.read()
 
 
-@pytest.mark.parametrize("seed,site,n", [(0, 0, 20), (1234, 7_000_000_123, 50), (2**63 + 5, 2**40 + 1, 4001), (7, 3, 1)])
-def test_device_index_stream_matches_oracle(seed, site, n):
+@pytest.mark.parametrize("seed,site,n", [(0, 0, 20), (1234, 7_000_000_123, 50), (2**63 + 5, 2**40 + 1, 4001), (7, 3, 1),
+                                         (7, 3, 256), (7, 3, 257)])      # 256 | 257: paired / single index regimes
+@pytest.mark.parametrize("n_samples", [20, 7])
+def test_device_index_stream_matches_oracle(seed, site, n, n_samples):
     from oracle import sample_indices
-    got = engine("HCT116_RNA002").sample_indices(seed, site, n, 257, 20).cpu().numpy()
-    want = sample_indices(seed, site, n, 257, 20)
+    got = engine("HCT116_RNA002").sample_indices(seed, site, n, 257, n_samples).cpu().numpy()
+    want = sample_indices(seed, site, n, 257, n_samples)
     assert np.array_equal(got.astype(np.int64), want)
 
 
@@ -159,6 +161,8 @@ def _random_case(rng, n_reads_list, n_kmer=66):
     ([30] * 11, 200, 7),                              # generic n_samples
     ([30] * 11, 200, 1),
     ([600] * 3 + [20] * 100, 128, 20),                # multi-chunk tiles
+    ([256, 257, 255, 300, 20], 96, 20),               # paired / single index regimes side by side
+    ([256, 257, 40], 96, 5),                          # odd n_samples in the paired regime
 ])
 def test_edge_cases_vs_oracle(n_reads_list, n_iters, n_samples):
     from oracle import mil_inference

@@ -37,8 +37,12 @@ def test_sample_indices_range_and_determinism():
     assert np.array_equal(sample_indices(5, 9, 37, 8, 20), sample_indices(5, 9, 37, 2048, 20)[:8])
     assert block_layout(1000) == (8, 4) and block_layout(2048) == (8, 8) and block_layout(10000) == (8, 40)
     assert block_layout(16384) == (8, 64) and block_layout(16385) == (9, 57) and block_layout(1) == (8, 1)
-    # the first round of every lane is the first n_samples draws of its generator
+    # the first round of every lane is the first n_samples draws of its generator (both regimes)
     assert np.array_equal(sample_indices(5, 9, 37, 32, 7), sample_indices(5, 9, 37, 32, 8)[:, :7])
+    assert np.array_equal(sample_indices(5, 9, 300, 32, 7), sample_indices(5, 9, 300, 32, 8)[:, :7])
+    # paired regime (n_reads <= 256): even draws are the single-regime draws of every second word
+    a = sample_indices(5, 9, 256, 32, 20)
+    assert a.min() >= 0 and a.max() < 256 and len(np.unique(a)) > 200
     # vectorised == per-site
     many = sample_indices_many(5, [9, 2**33 + 3], [37, 41], 300, 20)
     assert np.array_equal(many[0], sample_indices(5, 9, 37, 300, 20))
@@ -72,11 +76,16 @@ def test_sample_indices_lanes_and_rounds_are_uncorrelated():
 
 
 def test_sample_indices_uniform():
-    idx = sample_indices(0, 11, 50, 20000, 20).ravel()
-    counts = np.bincount(idx, minlength=50)
-    expected = len(idx) / 50
-    chi2 = ((counts - expected) ** 2 / expected).sum()
-    assert chi2 < 100.0  # 49 dof; P(chi2 > 100) ~ 2e-5
+    for n, dof_bound in ((50, 100.0), (256, 370.0), (300, 420.0)):     # paired regime (first and second halves) and single
+        idx = sample_indices(0, 11, n, 20000, 20)
+        for part in (idx[:, 0::2].ravel(), idx[:, 1::2].ravel()):
+            counts = np.bincount(part, minlength=n)
+            expected = len(part) / n
+            chi2 = ((counts - expected) ** 2 / expected).sum()
+            assert chi2 < dof_bound, (n, chi2)                          # P(chi2_{n-1} > bound) ~ 1e-5
+    # the two indices drawn from one word are uncorrelated
+    idx = sample_indices(1, 3, 64, 4000, 20).astype(np.float64)
+    assert abs(np.corrcoef(idx[:, 0::2].ravel(), idx[:, 1::2].ravel())[0, 1]) < 0.01
 
 
 def test_mt19937_replay_matches_numpy_choice():
