@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-sites", type=int, default=20_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tile-reads", type=int, default=0, help="override the kernel's feature rows per tile (0 = automatic)")
     ap.add_argument("--ragged", action="store_true", help="robustness run: lognormal n_reads (median 33, clip [20, 1000]) "
                     "instead of the constant --reads of the headline job (SURVEY.md section 8d)")
     return ap.parse_args()
@@ -215,8 +216,8 @@ def main():
     feats_h, off_h, kmer_h = synth_shard(sa, sb, a.reads, 1, a.ragged)
     thr = MODELS[a.model][1]
     eng = MilEngine(W.from_npz(os.path.join(ROOT, "m6anet_b200", "assets", "model_states", MODELS[a.model][0])), dev)
-    if a.ragged:
-        eng.set_tile_reads(1024)    # what the host path selects by itself for uneven read counts
+    if a.tile_reads:
+        eng.set_tile_reads(a.tile_reads)
 
     feats_p = torch.from_numpy(feats_h).pin_memory()
     off_p = torch.from_numpy(off_h).pin_memory()

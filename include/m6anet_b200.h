@@ -80,8 +80,8 @@ const char *m6a_strerror(int status);
  * device (synchronous).  The model may be used from any stream of that device. */
 int m6a_model_create(const m6a_weights_t *w, m6a_model_t **out);
 int m6a_model_destroy(m6a_model_t *model);
-/* Target feature rows per tile of the device call (default 512; 0 restores the default).  Sites with very
- * uneven read counts are scored faster with ~1024; m6a_mil_infer_host_f32 chooses automatically. */
+/* Feature rows per tile of the device call, 64..4096; 0 (default) = automatic: a multiple of the site depth close to
+ * 1000 rows (500 for small jobs).  Tiles are read-balanced: tile t holds the sites whose first row is in [t*T, (t+1)*T). */
 int m6a_model_set_tile_reads(m6a_model_t *model, int32_t tile_reads);
 
 /*
@@ -173,8 +173,8 @@ int m6a_write_indiv_csv(int32_t fd, int64_t n_sites, const char *tx_buf, const i
                         const int32_t *read_rep, const float *read_prob, int32_t n_threads);
 
 /* Launch geometry of the last m6a_mil_infer_f32 call on this thread (for bench/roofline
- * reporting): grid, block, dynamic smem bytes, sites per tile, number of kernel launches. */
-int m6a_last_launch(int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *sites_per_tile,
+ * reporting): grid, block, dynamic smem bytes, feature rows per tile, number of kernel launches. */
+int m6a_last_launch(int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *tile_reads,
                     int32_t *n_launches);
 
 #ifdef __cplusplus

@@ -29,7 +29,7 @@ struct m6a_model {
   void* d_ctab;
   int device;
   int n_sms;
-  int tile_reads = kTileReads;   // target feature rows per tile (m6a_model_set_tile_reads)
+  int tile_reads = 0;            // feature rows per tile; 0 = automatic (m6a_model_set_tile_reads)
   HostSlot slots[kHostSlots];
   std::mutex ws_mutex;
 };
@@ -132,8 +132,7 @@ extern "C" int m6a_model_create(const m6a_weights_t* w, m6a_model_t** out) {
 
 extern "C" int m6a_model_set_tile_reads(m6a_model_t* model, int32_t tile_reads) {
   if (!model) return M6A_EINVAL;
-  if (tile_reads == 0) tile_reads = kTileReads;
-  if (tile_reads < 32 || tile_reads > kQCap) return M6A_EINVAL;
+  if (tile_reads != 0 && (tile_reads < 64 || tile_reads > kQCap)) return M6A_EINVAL;
   model->tile_reads = tile_reads;
   return M6A_OK;
 }
@@ -147,10 +146,18 @@ extern "C" int m6a_model_destroy(m6a_model_t* model) {
   return M6A_OK;
 }
 
-static int sites_per_tile_for(long long n_sites, long long total_reads, int tile_reads) {
-  const long long avg = std::max<long long>(1, (total_reads + n_sites - 1) / std::max<long long>(1, n_sites));
-  long long g = tile_reads / avg;
-  return static_cast<int>(std::min<long long>(kSitesPerTileMax, std::max<long long>(1, g)));
+// Rows per tile when the caller did not fix it.  Tiles are cut at multiples of T rows (tile_bounds_kernel), so for
+// constant-depth sites T must be a multiple of the depth or every other tile spills a few rows into an extra chunk
+// (1 M x 50 reads: T = 500 or 1000 -> 18.2 ms, T = 512 -> 20.1 ms); uneven sites want ~1000 rows (19.5 ms vs 22.7 ms at
+// 512).  Small jobs use ~500 to keep at least ~48 tiles per CTA (tail imbalance of the persistent grid).
+static int auto_tile_reads(long long n_sites, long long total_reads, int n_sms) {
+  long long base = kChunkReads * 2 - 24;   // 1000 with 512-row chunks
+  if (total_reads / base < 48ll * n_sms * kCtasPerSm) base = kChunkReads - 12;   // 500
+  if (n_sites > 0 && total_reads % n_sites == 0) {
+    const long long depth = total_reads / n_sites;
+    if (depth >= 1 && depth <= base) base = (base / depth) * depth;
+  }
+  return static_cast<int>(std::max<long long>(64, std::min<long long>(base, kQCap)));
 }
 
 static int infer_device_impl(const m6a_model_t* model, int tile_reads, const float* feats, const int64_t* read_off,
@@ -177,8 +184,15 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
   a.site_prob = site_prob;
   a.mod_count = mod_count;
   a.n_sites = n_sites;
-  a.sites_per_tile = sites_per_tile_for(n_sites, total_reads, tile_reads);
-  a.n_tiles = (n_sites + a.sites_per_tile - 1) / a.sites_per_tile;
+  // read-balanced tiles: tile t = sites whose first row lies in [t*T, (t+1)*T); boundaries by a prepass into a
+  // stream-ordered scratch allocation (freed right after the launches, still in stream order)
+  if (tile_reads <= 0) tile_reads = auto_tile_reads(n_sites, total_reads, model->n_sms);
+  a.tile_reads = tile_reads;
+  a.n_tiles = total_reads / tile_reads + 1;
+  long long* d_bounds = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  M6A_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_bounds), static_cast<size_t>(a.n_tiles + 1) * sizeof(long long), st));
+  a.tile_bounds = d_bounds;
   a.site_id_base = site_id_base;
   a.feats_bytes = static_cast<unsigned long long>(total_reads) * (kNSig * sizeof(float));
   a.seed = seed;
@@ -189,10 +203,13 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
   a.feats_tma_ok = (reinterpret_cast<uintptr_t>(feats) & 15u) == 0;
 
   LaunchInfo info;
-  cudaError_t e = launch_mil_infer(a, &model->host_image, model->n_sms, static_cast<cudaStream_t>(stream), &info);
+  cudaError_t e = launch_tile_bounds(read_off, n_sites, a.n_tiles, tile_reads, d_bounds, st);
+  if (e == cudaSuccess) e = launch_mil_infer(a, &model->host_image, model->n_sms, st, &info);
+  const cudaError_t e2 = cudaFreeAsync(d_bounds, st);
   if (e != cudaSuccess) return static_cast<int>(e);
+  if (e2 != cudaSuccess) return static_cast<int>(e2);
   g_last = info;
-  g_last_launches = 1;
+  g_last_launches = 2;   // tile_bounds_kernel + mil_infer_kernel
   return M6A_OK;
 }
 
@@ -214,12 +231,12 @@ extern "C" int m6a_sample_indices(uint64_t seed, int64_t site_id, int32_t n_read
   return e == cudaSuccess ? M6A_OK : static_cast<int>(e);
 }
 
-extern "C" int m6a_last_launch(int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* sites_per_tile,
+extern "C" int m6a_last_launch(int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* tile_reads,
                                int32_t* n_launches) {
   if (grid) *grid = g_last.grid;
   if (block) *block = g_last.block;
   if (smem_bytes) *smem_bytes = g_last.smem_bytes;
-  if (sites_per_tile) *sites_per_tile = g_last.sites_per_tile;
+  if (tile_reads) *tile_reads = g_last.tile_reads;
   if (n_launches) *n_launches = g_last_launches;
   return M6A_OK;
 }
@@ -310,15 +327,7 @@ extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model_c, const float* f
   }
 
   std::lock_guard<std::mutex> guard(model->ws_mutex);
-  // Ragged sites (real data: 20..1000+ reads) are scored ~5% faster with tiles of ~1024 rows, constant-depth
-  // sites ~1% faster with ~512 (profiles/r01_tile_size_ab.txt); the host path sees read_off and picks.
-  int tile_reads = model->tile_reads;
-  if (tile_reads == kTileReads) {
-    int64_t max_n = 0;
-    for (int64_t i = 0; i < n_sites; ++i) max_n = std::max(max_n, read_off[i + 1] - read_off[i]);
-    const double mean_n = static_cast<double>(total_reads) / static_cast<double>(n_sites);
-    if (static_cast<double>(max_n) > 1.25 * mean_n + 1.0) tile_reads = std::min(1024, kQCap);
-  }
+  const int tile_reads = model->tile_reads;
   const int n_slots = std::min(kHostSlots, n_chunks);
   for (int s = 0; s < n_slots; ++s) M6A_CUDA(slot_reserve(model->slots[s], max_sites, std::max<int64_t>(1, max_reads)));
 

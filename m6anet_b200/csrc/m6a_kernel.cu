@@ -6,7 +6,9 @@
 //   group_results / mod_ratio                                          utils/inference_utils.py:48-53
 //   calculate_site_proba (_calculate_site_proba)                       utils/inference_utils.py:54,74-104
 //
-// Work decomposition (one persistent CTA loops over tiles; a tile = G consecutive sites):
+// Work decomposition (one persistent CTA loops over tiles; a tile = the consecutive sites whose first feature row
+// lies in [t*T, (t+1)*T), T = tile_reads, so every tile carries about T rows however uneven the sites are;
+// the boundaries come from a prepass, tile_bounds_kernel):
 //   stage   the tile's feature rows are one contiguous byte range of `feats` -> one cp.async.bulk
 //           (TMA, mbarrier completion) per chunk of kChunkReads rows into shared memory
 //   phase A thread-per-read (kReadsPerThread reads per thread), hidden units two at a time with
@@ -293,8 +295,10 @@ mil_infer_kernel(const KernelArgs a) {
   const float n_iters_f = static_cast<float>(a.n_iters);
 
   for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const long long s0 = tile * a.sites_per_tile;
-    const int ns = static_cast<int>(min(static_cast<long long>(a.sites_per_tile), a.n_sites - s0));
+   // a tile normally holds <= kSitesPerTileMax sites; more (very short sites) are taken in slices
+   const long long tile_s0 = a.tile_bounds[tile], tile_s1 = a.tile_bounds[tile + 1];
+   for (long long s0 = tile_s0; s0 < tile_s1; s0 += kSitesPerTileMax) {
+    const int ns = static_cast<int>(min(static_cast<long long>(kSitesPerTileMax), tile_s1 - s0));
     const long long r0 = a.read_off[s0];
 
     // ---- tile header: local CSR offsets, k-mer ids, counters ------------------------------------
@@ -458,9 +462,28 @@ mil_infer_kernel(const KernelArgs a) {
       a.mod_count[s0 + tid] = sm.cnt[tid];
     }
     __syncthreads();  // roff/cnt/partial are rewritten by the next tile
+   }
   }
 
   if (!weights_ready) mbar_wait(&sm.bar_w, 0);  // never leave with a bulk copy in flight
+}
+
+// Prepass: tile t starts at the first site whose first feature row is >= t * tile_reads (binary search over read_off).
+__global__ void tile_bounds_kernel(const int64_t* __restrict__ read_off, long long n_sites, long long n_tiles, int tile_reads,
+                                   long long* __restrict__ tile_bounds) {
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t > n_tiles) return;
+  if (t == n_tiles) {
+    tile_bounds[t] = n_sites;
+    return;
+  }
+  const long long target = t * tile_reads;
+  long long lo = 0, hi = n_sites;            // first s in [0, n_sites) with read_off[s] >= target
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (read_off[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  tile_bounds[t] = lo;
 }
 
 __global__ void sample_indices_kernel(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
@@ -512,7 +535,7 @@ cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image,
     info->grid = static_cast<int>(grid);
     info->block = kThreads;
     info->smem_bytes = smem;
-    info->sites_per_tile = a.sites_per_tile;
+    info->tile_reads = a.tile_reads;
   }
 #if M6A_WEIGHTS_CONST
   if (fast)
@@ -526,6 +549,14 @@ cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image,
   else
     kgen<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a);
 #endif
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tile_bounds(const int64_t* read_off, long long n_sites, long long n_tiles, int tile_reads,
+                               long long* tile_bounds, cudaStream_t stream) {
+  const long long n = n_tiles + 1;
+  tile_bounds_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(read_off, n_sites, n_tiles, tile_reads,
+                                                                               tile_bounds);
   return cudaGetLastError();
 }
 

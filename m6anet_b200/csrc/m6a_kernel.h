@@ -19,7 +19,7 @@ namespace m6a {
 #define M6A_CTAS 2
 #endif
 #ifndef M6A_GMAX
-#define M6A_GMAX 32
+#define M6A_GMAX 64
 #endif
 #ifndef M6A_QCAP
 #define M6A_QCAP 4096
@@ -39,7 +39,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kReadsPerThread = M6A_RPT;
 constexpr int kCtasPerSm = M6A_CTAS;
 constexpr int kChunkReads = kThreads * kReadsPerThread;  // feature rows staged per bulk copy
-constexpr int kTileReads = M6A_TILE_READS;               // target reads per tile (sites_per_tile = kTileReads / mean reads)
+constexpr int kTileReads = M6A_TILE_READS;               // (legacy tunable; tiles are sized by auto_tile_reads in m6a_api.cu)
 constexpr int kSitesPerTileMax = M6A_GMAX;
 constexpr int kQCap = M6A_QCAP;         // q = 1-p entries kept in shared memory per tile
 constexpr int kCStride = kH1Max;        // even (float2 loads); 152 mod 32 = 24 keeps neighbouring site rows on distinct banks
@@ -63,12 +63,13 @@ struct KernelArgs {
   float* read_prob;
   float* site_prob;
   int32_t* mod_count;
+  const long long* tile_bounds;   // [n_tiles + 1] first site of every tile (prepass: lower_bound(read_off, t * tile_reads))
   long long n_sites;
   long long n_tiles;
   long long site_id_base;
   unsigned long long feats_bytes;
   unsigned long long seed;
-  int sites_per_tile;
+  int tile_reads;      // target feature rows per tile
   int n_samples;
   int n_iters;
   int n_blocks;        // ceil(n_iters / (32 * iters_per_lane)) <= 64
@@ -78,12 +79,14 @@ struct KernelArgs {
 };
 
 struct LaunchInfo {
-  int grid, block, smem_bytes, sites_per_tile;
+  int grid, block, smem_bytes, tile_reads;
 };
 
 size_t smem_bytes();
 cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image, int n_sms, cudaStream_t stream,
                              LaunchInfo* info);
+cudaError_t launch_tile_bounds(const int64_t* read_off, long long n_sites, long long n_tiles, int tile_reads,
+                               long long* tile_bounds, cudaStream_t stream);
 cudaError_t launch_sample_indices(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
                                   int32_t* out, cudaStream_t stream);
 

@@ -45,7 +45,7 @@ class MilEngine:
         self._handle = handle
 
     def set_tile_reads(self, tile_reads: int = 0):
-        """Target feature rows per tile of infer_device (0 = default 512; ~1024 suits very uneven read counts)."""
+        """Feature rows per tile (64..4096); 0 = automatic (a multiple of the site depth near 1000 rows)."""
         _cabi.check(self._lib.m6a_model_set_tile_reads(self._handle, int(tile_reads)), "m6a_model_set_tile_reads")
 
     def close(self):
@@ -128,4 +128,4 @@ class MilEngine:
     def last_launch(self) -> dict:
         v = [C.c_int32() for _ in range(5)]
         self._lib.m6a_last_launch(*[C.byref(x) for x in v])
-        return dict(zip(("grid", "block", "smem_bytes", "sites_per_tile", "n_launches"), (x.value for x in v)))
+        return dict(zip(("grid", "block", "smem_bytes", "tile_reads", "n_launches"), (x.value for x in v)))
