@@ -204,8 +204,19 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner with printf on fd 1 at communicator creation; stdout must carry only the JSON
+        # line, so fd 1 points at stderr until the first collective has run.
+        sys.stdout.flush()
+        saved_fd1 = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd1, 1)
+            os.close(saved_fd1)
     n_gpus = world
 
     # ---- shard: contiguous site ranges, equal read counts (constant n_reads) -------------------------
@@ -268,10 +279,17 @@ def main():
     elapsed_ms = ev[0].elapsed_time(ev[1])
     kernel_ms = [k0.elapsed_time(k1) for k0, k1 in kev]
     launch = eng.last_launch()
+    per_rank = None
     if world > 1:
         t = torch.tensor([elapsed_ms, max(kernel_ms)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t[0])
+        mine = torch.tensor([sum(kernel_ms) / len(kernel_ms), float(clocks["sm_mhz"] or 0), float(len(clocks["reasons"]))],
+                            dtype=torch.float64, device=dev)
+        allr = torch.empty((world, 3), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = {"kernel_ms": [round(float(v), 3) for v in allr[:, 0]], "sm_mhz": [float(v) for v in allr[:, 1]],
+                    "n_throttle_reasons": [int(v) for v in allr[:, 2]]}
     ms_per_step = elapsed_ms / a.steps
     value = a.sites / (ms_per_step * 1e-3)
 
@@ -346,7 +364,7 @@ def main():
                        "l2": f"inputs ({feats_h.nbytes / 1e6:.0f} MB/rank) larger than L2" if feats_h.nbytes > 126e6
                              else "inputs smaller than L2 (not flushed)",
                        "launch": launch},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "per_rank": per_rank,
             "gpu_launches": a.steps * launch["n_launches"],
         }
         print(json.dumps(line), flush=True)

@@ -153,7 +153,6 @@ def run_inference(model: MILModel, dl, args):
         import torch.distributed as dist
         if not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=dev)
     seed = int(getattr(args, "seed", 0))
     n_iters = int(args.num_iterations)
