@@ -107,12 +107,18 @@ int m6a_model_set_tile_reads(m6a_model_t *model, int32_t tile_reads);
  *   site_prob   [n_sites] float32; NaN for a site without reads
  *   mod_count   [n_sites] int32 number of reads with p >= read_threshold
  *               (mod_ratio = mod_count / n_reads, formed by the host in float64 like np.mean)
+ * scratch
+ *   workspace   DEVICE buffer of at least m6a_mil_workspace_bytes(total_reads) bytes, 8-byte aligned, owned by the
+ *               caller and private to this call until it has completed on `stream` (tile boundaries of the prepass).
+ *               The library allocates nothing on this path.
  */
+int64_t m6a_mil_workspace_bytes(int64_t total_reads);
 int m6a_mil_infer_f32(const m6a_model_t *model, const float *feats, const int64_t *read_off,
                       const int32_t *kmer_idx, int64_t n_sites, int64_t total_reads,
                       int64_t site_id_base, int32_t n_samples, int32_t n_iters, uint64_t seed,
                       const uint16_t *sample_idx, float read_threshold, float *read_prob,
-                      float *site_prob, int32_t *mod_count, void *stream);
+                      float *site_prob, int32_t *mod_count, void *workspace, int64_t workspace_bytes,
+                      void *stream);
 
 /*
  * Same computation with HOST buffers (read_off[0] must be 0 here).  Sites are cut into

@@ -13,11 +13,12 @@
 
 using namespace m6a;
 
+extern "C" int64_t m6a_mil_workspace_bytes(int64_t total_reads);
 constexpr int kHostSlots = 3;
 struct HostSlot {   // one stage of the host-buffer pipeline (m6a_mil_infer_host_f32)
   cudaStream_t stream = nullptr;
-  void *d_feats = nullptr, *d_off = nullptr, *d_kmer = nullptr, *d_rp = nullptr, *d_sp = nullptr, *d_mc = nullptr;
-  size_t cap_feats = 0, cap_off = 0, cap_kmer = 0, cap_rp = 0, cap_sp = 0, cap_mc = 0;
+  void *d_feats = nullptr, *d_off = nullptr, *d_kmer = nullptr, *d_rp = nullptr, *d_sp = nullptr, *d_mc = nullptr, *d_ws = nullptr;
+  size_t cap_feats = 0, cap_off = 0, cap_kmer = 0, cap_rp = 0, cap_sp = 0, cap_mc = 0, cap_ws = 0;
   int64_t* h_off = nullptr;   // pinned staging for re-based offsets
   size_t cap_hoff = 0;
 };
@@ -164,7 +165,7 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
                              const int32_t* kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
                              int32_t n_samples, int32_t n_iters, uint64_t seed, const uint16_t* sample_idx,
                              float read_threshold, float* read_prob, float* site_prob, int32_t* mod_count,
-                             void* stream) {
+                             void* workspace, int64_t workspace_bytes, void* stream) {
   if (!model || n_sites < 0 || total_reads < 0) return M6A_EINVAL;
   if (n_samples < 1 || n_samples > 64 || n_iters < 1) return M6A_EINVAL;
   if (n_sites == 0) return M6A_OK;
@@ -184,14 +185,15 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
   a.site_prob = site_prob;
   a.mod_count = mod_count;
   a.n_sites = n_sites;
-  // read-balanced tiles: tile t = sites whose first row lies in [t*T, (t+1)*T); boundaries by a prepass into a
-  // stream-ordered scratch allocation (freed right after the launches, still in stream order)
+  // read-balanced tiles: tile t = sites whose first row lies in [t*T, (t+1)*T); boundaries by a prepass into the
+  // caller's workspace (the library allocates nothing on this path)
   if (tile_reads <= 0) tile_reads = auto_tile_reads(n_sites, total_reads, model->n_sms);
   a.tile_reads = tile_reads;
   a.n_tiles = total_reads / tile_reads + 1;
-  long long* d_bounds = nullptr;
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 7u)) return workspace ? M6A_EALIGN : M6A_EINVAL;
+  if (workspace_bytes < static_cast<int64_t>((a.n_tiles + 1) * sizeof(long long))) return M6A_EINVAL;
+  long long* d_bounds = static_cast<long long*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  M6A_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_bounds), static_cast<size_t>(a.n_tiles + 1) * sizeof(long long), st));
   a.tile_bounds = d_bounds;
   a.site_id_base = site_id_base;
   a.feats_bytes = static_cast<unsigned long long>(total_reads) * (kNSig * sizeof(float));
@@ -205,9 +207,7 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
   LaunchInfo info;
   cudaError_t e = launch_tile_bounds(read_off, n_sites, a.n_tiles, tile_reads, d_bounds, st);
   if (e == cudaSuccess) e = launch_mil_infer(a, &model->host_image, model->n_sms, st, &info);
-  const cudaError_t e2 = cudaFreeAsync(d_bounds, st);
   if (e != cudaSuccess) return static_cast<int>(e);
-  if (e2 != cudaSuccess) return static_cast<int>(e2);
   g_last = info;
   g_last_launches = 2;   // tile_bounds_kernel + mil_infer_kernel
   return M6A_OK;
@@ -217,10 +217,16 @@ extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, c
                                  const int32_t* kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
                                  int32_t n_samples, int32_t n_iters, uint64_t seed, const uint16_t* sample_idx,
                                  float read_threshold, float* read_prob, float* site_prob, int32_t* mod_count,
-                                 void* stream) {
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
   if (!model) return M6A_EINVAL;
   return infer_device_impl(model, model->tile_reads, feats, read_off, kmer_idx, n_sites, total_reads, site_id_base, n_samples,
-                           n_iters, seed, sample_idx, read_threshold, read_prob, site_prob, mod_count, stream);
+                           n_iters, seed, sample_idx, read_threshold, read_prob, site_prob, mod_count, workspace,
+                           workspace_bytes, stream);
+}
+
+extern "C" int64_t m6a_mil_workspace_bytes(int64_t total_reads) {
+  if (total_reads < 0) return 0;
+  return (total_reads / 64 + 2) * static_cast<int64_t>(sizeof(long long));   // tiles hold >= 64 rows
 }
 
 extern "C" int m6a_sample_indices(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters, int32_t n_samples,
@@ -268,6 +274,7 @@ static cudaError_t slot_reserve(HostSlot& sl, int64_t max_sites, int64_t max_rea
   if (e == cudaSuccess) e = ensure_bytes(&sl.d_kmer, &sl.cap_kmer, static_cast<size_t>(max_sites) * kKmerPos * sizeof(int32_t));
   if (e == cudaSuccess) e = ensure_bytes(&sl.d_sp, &sl.cap_sp, static_cast<size_t>(max_sites) * sizeof(float));
   if (e == cudaSuccess) e = ensure_bytes(&sl.d_mc, &sl.cap_mc, static_cast<size_t>(max_sites) * sizeof(int32_t));
+  if (e == cudaSuccess) e = ensure_bytes(&sl.d_ws, &sl.cap_ws, static_cast<size_t>(m6a_mil_workspace_bytes(max_reads)));
   if (e == cudaSuccess && static_cast<size_t>(max_sites + 1) > sl.cap_hoff) {
     if (sl.h_off) cudaFreeHost(sl.h_off);
     sl.h_off = nullptr;
@@ -284,7 +291,7 @@ void m6a_release_workspace(m6a_model* m) {
     HostSlot& sl = m->slots[s];
     if (sl.stream) cudaStreamSynchronize(sl.stream);
     cudaFree(sl.d_feats); cudaFree(sl.d_off); cudaFree(sl.d_kmer);
-    cudaFree(sl.d_rp); cudaFree(sl.d_sp); cudaFree(sl.d_mc);
+    cudaFree(sl.d_rp); cudaFree(sl.d_sp); cudaFree(sl.d_mc); cudaFree(sl.d_ws);
     if (sl.h_off) cudaFreeHost(sl.h_off);
     if (sl.stream) cudaStreamDestroy(sl.stream);
     sl = HostSlot();
@@ -355,7 +362,8 @@ extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model_c, const float* f
     rc = infer_device_impl(model, tile_reads, static_cast<const float*>(sl.d_feats), static_cast<const int64_t*>(sl.d_off),
                            kmer_idx ? static_cast<const int32_t*>(sl.d_kmer) : nullptr, ns, nr, site_id_base + sa,
                            n_samples, n_iters, seed, nullptr, read_threshold, static_cast<float*>(sl.d_rp),
-                           static_cast<float*>(sl.d_sp), static_cast<int32_t*>(sl.d_mc), sl.stream);
+                           static_cast<float*>(sl.d_sp), static_cast<int32_t*>(sl.d_mc), sl.d_ws,
+                           static_cast<int64_t>(sl.cap_ws), sl.stream);
     if (rc != M6A_OK) break;
     ++launches;
     if (nr > 0) e = cudaMemcpyAsync(read_prob + ra, sl.d_rp, nr * sizeof(float), cudaMemcpyDeviceToHost, sl.stream);

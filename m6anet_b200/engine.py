@@ -83,13 +83,19 @@ class MilEngine:
             mod_count = torch.empty(n_sites, dtype=torch.int32, device=self.device)
         else:
             read_prob, site_prob, mod_count = out
+        # scratch for the tile-boundary prepass; torch's caching allocator keeps it stream-safe and cheap
+        ws_bytes = int(self._lib.m6a_mil_workspace_bytes(total_reads))
+        workspace = torch.empty(ws_bytes // 8, dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device) if stream is None else stream
+            if stream is not None:
+                workspace.record_stream(st)
             rc = self._lib.m6a_mil_infer_f32(
                 self._handle, feats.data_ptr(), read_off.data_ptr(), None if kmer_idx is None else kmer_idx.data_ptr(),
                 n_sites, total_reads, site_id_base, n_samples, n_iters, seed & 0xFFFFFFFFFFFFFFFF,
                 None if sample_idx is None else sample_idx.data_ptr(), read_threshold,
-                read_prob.data_ptr(), site_prob.data_ptr(), mod_count.data_ptr(), st.cuda_stream)
+                read_prob.data_ptr(), site_prob.data_ptr(), mod_count.data_ptr(), workspace.data_ptr(), ws_bytes,
+                st.cuda_stream)
         _cabi.check(rc, "m6a_mil_infer_f32")
         return read_prob, site_prob, mod_count
 
