@@ -16,10 +16,12 @@
 //           frees issue slots for the integer work of phase B running in the co-resident CTA):
 //             (h_j0,h_j1) = relu(c_site[j0:j1] + sum_k (w1[j0,k],w1[j1,k]) * x_k)     9 FFMA2
 //             acc[0:32]  += w2[:,j0] * h_j0 ; acc[0:32] += w2[:,j1] * h_j1            32 FFMA2
-//           weights come from shared memory at warp-uniform addresses (LDS.128 broadcast);
+//           the weight image is a __grid_constant__ kernel parameter: LDCU.64 into uniform registers, FFMA2 with a
+//           uniform-register operand -- no shared-memory traffic, no vector registers for weights (m6a_layout.h);
 //           the k-mer embedding part of Linear-1 is a per-site constant c_site (m6a_layout.h)
 //   phase B warp-per-(site, block of 32*ipl iterations): every lane owns a Philox-seeded MWC64X
-//           stream (m6a_rng.cuh) and runs its ipl iterations: 20 x (draw, mulhi, LDS q[idx], FMUL)
+//           stream (m6a_rng.cuh) and runs its ipl iterations: 20 x (draw, index, LDS q[idx], FMUL),
+//           two indices per 32-bit word for sites with <= 256 reads
 //   final   butterfly sum per block, ordered sum of block partials / n_iters -> site_prob
 // The summation order and the index streams are functions of (seed, site id, n_iters) only -- not of
 // tiling, grid or GPU count -- so a site's result is bit-identical however the sites are sharded.

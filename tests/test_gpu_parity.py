@@ -235,6 +235,23 @@ def test_invalid_arguments_are_rejected(synthetic_inputs):
     bad = W.EncoderWeights(w.emb, w.w1, w.b1, w.w2[:16], w.b2[:16], w.w3[:16], w.b3)
     with pytest.raises(M6AError):
         MilEngine(bad, "cuda:0")
+    # the caller-owned workspace is validated: missing or too small -> M6A_EINVAL, nothing is launched
+    import ctypes as C
+    import torch
+    from m6anet_b200 import _cabi
+    L = _cabi.lib()
+    f = torch.zeros((40, 9), device="cuda:0")
+    off = torch.tensor([0, 20, 40], dtype=torch.int64, device="cuda:0")
+    k = torch.zeros((2, 3), dtype=torch.int32, device="cuda:0")
+    rp, sp, mc = torch.empty(40, device="cuda:0"), torch.empty(2, device="cuda:0"), torch.empty(2, dtype=torch.int32, device="cuda:0")
+    ws = torch.empty(4, dtype=torch.int64, device="cuda:0")
+    args = lambda wsp, wsb: (eng._handle, f.data_ptr(), off.data_ptr(), k.data_ptr(), 2, 40, 0, 20, 10, 0, None, 0.5,
+                             rp.data_ptr(), sp.data_ptr(), mc.data_ptr(), wsp, wsb, None)
+    assert L.m6a_mil_workspace_bytes(40) == 16 and L.m6a_mil_workspace_bytes(10**6) >= (10**6 // 1000 + 2) * 8
+    assert L.m6a_mil_infer_f32(*args(None, 0)) == -1
+    assert L.m6a_mil_infer_f32(*args(ws.data_ptr(), 8)) == -1
+    assert L.m6a_mil_infer_f32(*args(ws.data_ptr(), 32)) == 0
+    torch.cuda.synchronize()
 
 
 def _read_probs_float64(params, feats, kmer_rows):
