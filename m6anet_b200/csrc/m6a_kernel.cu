@@ -98,7 +98,7 @@ __device__ __forceinline__ float warp_butterfly_sum(float v) {
 // ---- one lane's share of a (site, block): ipl iterations of 1 - prod_{s<n_samples} q[idx_s] ------
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");   // ordered after the phase barrier
   return v;
 }
 
@@ -511,7 +511,10 @@ __global__ void sample_indices_kernel(uint64_t seed, uint64_t site_id, uint32_t 
 }
 
 // ---- host-side launchers ---------------------------------------------------------------------------
-static int g_max_ctas_per_sm[2] = {-1, -1};
+// occupancy / max-dynamic-smem attribute are per (device, kernel instantiation)
+constexpr int kMaxDevices = 64;
+static int g_max_ctas_per_sm[kMaxDevices][2];
+static bool g_attr_done[kMaxDevices][2];
 
 cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image, int n_sms, cudaStream_t stream,
                              LaunchInfo* info) {
@@ -520,8 +523,12 @@ cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image,
   auto kgen = mil_infer_kernel<0>;
   const void* fn = fast ? reinterpret_cast<const void*>(kfast) : reinterpret_cast<const void*>(kgen);
   const int smem = static_cast<int>(sizeof(Smem));
-  int& occ = g_max_ctas_per_sm[fast ? 0 : 1];
-  if (occ < 0) {
+  int dev = 0;
+  cudaError_t de = cudaGetDevice(&dev);
+  if (de != cudaSuccess) return de;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  int& occ = g_max_ctas_per_sm[dev][fast ? 0 : 1];
+  if (!g_attr_done[dev][fast ? 0 : 1]) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     int nb = 0;
@@ -529,6 +536,7 @@ cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image,
              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kgen, kThreads, smem);
     if (e != cudaSuccess) return e;
     occ = nb > 0 ? nb : 1;
+    g_attr_done[dev][fast ? 0 : 1] = true;
   }
   long long grid = static_cast<long long>(n_sms) * occ;
   if (grid > a.n_tiles) grid = a.n_tiles;

@@ -67,16 +67,25 @@ class MilEngine:
         Enqueues on `stream` (default: torch's current stream); returns (read_prob, site_prob, mod_count)
         CUDA tensors without synchronising."""
         torch = self._torch
-        assert feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()
-        assert read_off.is_cuda and read_off.dtype == torch.int64 and read_off.is_contiguous()
+
+        def need(cond, msg):
+            if not cond:
+                raise ValueError("MilEngine.infer_device: " + msg)
+
+        need(feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous() and feats.dim() == 2 and feats.shape[1] == 9,
+             "feats must be a contiguous float32 CUDA tensor [reads, 9]")
+        need(read_off.is_cuda and read_off.dtype == torch.int64 and read_off.is_contiguous() and read_off.numel() >= 1,
+             "read_off must be a contiguous int64 CUDA tensor [sites + 1]")
+        need(feats.device == self.device and read_off.device == self.device, f"tensors must live on {self.device}")
         n_sites = read_off.numel() - 1
         total_reads = feats.shape[0]
         if kmer_idx is not None:
-            assert kmer_idx.is_cuda and kmer_idx.dtype == torch.int32 and kmer_idx.is_contiguous()
-            assert kmer_idx.numel() == 3 * n_sites
+            need(kmer_idx.is_cuda and kmer_idx.dtype == torch.int32 and kmer_idx.is_contiguous() and kmer_idx.numel() == 3 * n_sites,
+                 "kmer_idx must be a contiguous int32 CUDA tensor [sites, 3]")
         if sample_idx is not None:
-            assert sample_idx.is_cuda and sample_idx.dtype == torch.uint16 and sample_idx.is_contiguous()
-            assert sample_idx.numel() == n_sites * n_iters * n_samples
+            need(sample_idx.is_cuda and sample_idx.dtype == torch.uint16 and sample_idx.is_contiguous()
+                 and sample_idx.numel() == n_sites * n_iters * n_samples,
+                 "sample_idx must be a contiguous uint16 CUDA tensor [sites, n_iters, n_samples]")
         if out is None:
             read_prob = torch.empty(total_reads, dtype=torch.float32, device=self.device)
             site_prob = torch.empty(n_sites, dtype=torch.float32, device=self.device)

@@ -223,6 +223,10 @@ def run_inference(model: MILModel, dl, args):
             all_sp.append(site_prob)
             all_mc.append(mod_count)
             q_out.put((batch, read_prob, site_prob, mod_count))
+    except BaseException as e:   # noqa: BLE001 - the GPU stage failed: stop the producer, then re-raise below
+        errors.insert(0, e)
+        while q_in.get() is not None:     # unblock an ingest thread waiting on the bounded queue
+            pass
     finally:
         q_out.put(None)
         t_in.join()
