@@ -75,6 +75,9 @@ typedef struct m6a_model m6a_model_t; /* opaque: packed weight image resident on
 
 int m6a_version(void);
 const char *m6a_strerror(int status);
+/* Thin wrappers of cudaGetDeviceCount / cudaSetDevice so that a host program needs no other CUDA binding. */
+int m6a_device_count(int32_t *count);
+int m6a_set_device(int32_t device);
 
 /* Packs the weights into the kernel's shared-memory image and uploads it to the current CUDA
  * device (synchronous).  The model may be used from any stream of that device. */

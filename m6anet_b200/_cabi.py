@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("M6A_LIB") or os.path.join(_HERE, "libm6anet_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 EXPORTS = (
-    "m6a_version", "m6a_strerror", "m6a_model_create", "m6a_model_destroy", "m6a_model_set_tile_reads", "m6a_mil_workspace_bytes",
+    "m6a_version", "m6a_strerror", "m6a_device_count", "m6a_set_device", "m6a_model_create", "m6a_model_destroy", "m6a_model_set_tile_reads", "m6a_mil_workspace_bytes",
     "m6a_mil_infer_f32",
     "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_last_launch", "m6a_ingest_parts", "m6a_write_site_csv",
     "m6a_write_indiv_csv",
@@ -72,6 +72,10 @@ def lib() -> C.CDLL:
     L.m6a_version.argtypes = []
     L.m6a_strerror.restype = C.c_char_p
     L.m6a_strerror.argtypes = [C.c_int]
+    L.m6a_device_count.restype = C.c_int
+    L.m6a_device_count.argtypes = [C.POINTER(i32)]
+    L.m6a_set_device.restype = C.c_int
+    L.m6a_set_device.argtypes = [i32]
     L.m6a_model_create.restype = C.c_int
     L.m6a_model_create.argtypes = [C.POINTER(M6AWeights), C.POINTER(vp)]
     L.m6a_model_destroy.restype = C.c_int
@@ -96,6 +100,30 @@ def lib() -> C.CDLL:
     L.m6a_write_indiv_csv.argtypes = [i32, i64, vp, vp, vp, vp, vp, vp, vp, i32]
     _lib = L
     return L
+
+
+def device_count() -> int:
+    """Number of visible CUDA devices (0 when there is no driver / GPU); does not import torch."""
+    n = C.c_int32(0)
+    lib().m6a_device_count(C.byref(n))
+    return int(n.value)
+
+
+def parse_device(device) -> int:
+    """'cuda' / 'cuda:N' / N / torch.device -> device index (None = current default 0)."""
+    if device is None:
+        return 0
+    if isinstance(device, int):
+        return device
+    idx = getattr(device, "index", None)
+    if hasattr(device, "type"):
+        if device.type != "cuda":
+            raise ValueError(f"m6anet_b200 needs a cuda device, got {device}")
+        return 0 if idx is None else int(idx)
+    text = str(device)
+    if not text.startswith("cuda"):
+        raise ValueError(f"m6anet_b200 needs a cuda device, got {device!r}")
+    return int(text.split(":", 1)[1]) if ":" in text else 0
 
 
 def check(status: int, where: str) -> None:

@@ -41,6 +41,19 @@ static thread_local int g_last_launches = 0;
 
 extern "C" int m6a_version(void) { return M6A_VERSION; }
 
+extern "C" int m6a_device_count(int32_t* count) {
+  if (!count) return M6A_EINVAL;
+  int n = 0;
+  const cudaError_t e = cudaGetDeviceCount(&n);
+  *count = (e == cudaSuccess) ? n : 0;
+  return e == cudaSuccess ? M6A_OK : static_cast<int>(e);
+}
+
+extern "C" int m6a_set_device(int32_t device) {
+  const cudaError_t e = cudaSetDevice(device);
+  return e == cudaSuccess ? M6A_OK : static_cast<int>(e);
+}
+
 extern "C" const char* m6a_strerror(int status) {
   switch (status) {
     case M6A_OK: return "ok";

@@ -21,17 +21,13 @@ class MilEngine:
     """One packed model resident on one CUDA device."""
 
     def __init__(self, weights: EncoderWeights, device: "int | str | None" = None):
-        import torch
-        if not torch.cuda.is_available():
-            raise RuntimeError("m6anet_b200 needs a CUDA device (the hot path has no CPU fallback)")
-        self._torch = torch
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        if self.device.type != "cuda":
-            raise ValueError(f"MilEngine needs a cuda device, got {self.device}")
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
-        self.weights = weights
         self._lib = _cabi.lib()
+        if _cabi.device_count() < 1:
+            raise RuntimeError("m6anet_b200 needs a CUDA device (the hot path has no CPU fallback)")
+        self.device_index = _cabi.parse_device(device)
+        if self.device_index >= _cabi.device_count():
+            raise ValueError(f"cuda:{self.device_index} is not visible ({_cabi.device_count()} device(s))")
+        self.weights = weights
         keep = {k: np.ascontiguousarray(getattr(weights, k), dtype=np.float32)
                 for k in ("w1", "b1", "w2", "b2", "w3", "b3")}
         emb = None if weights.emb is None else np.ascontiguousarray(weights.emb, dtype=np.float32)
@@ -40,9 +36,22 @@ class MilEngine:
                              n_kmer=weights.n_kmer, emb_dim=weights.emb_dim, n_sig=weights.n_sig,
                              h1=weights.h1, h2=weights.h2)
         handle = C.c_void_p()
-        with torch.cuda.device(self.device):
-            _cabi.check(self._lib.m6a_model_create(C.byref(w), C.byref(handle)), "m6a_model_create")
+        self._select()
+        _cabi.check(self._lib.m6a_model_create(C.byref(w), C.byref(handle)), "m6a_model_create")
         self._handle = handle
+
+    def _select(self):
+        """Make this engine's device current for the calling thread (cudaSetDevice)."""
+        _cabi.check(self._lib.m6a_set_device(self.device_index), "m6a_set_device")
+
+    @property
+    def _torch(self):
+        import torch       # only the tensor-facing calls need torch; the host-buffer path does not
+        return torch
+
+    @property
+    def device(self):
+        return self._torch.device("cuda", self.device_index)
 
     def set_tile_reads(self, tile_reads: int = 0):
         """Feature rows per tile (64..4096); 0 = automatic (a multiple of the site depth near 1000 rows)."""
@@ -124,10 +133,10 @@ class MilEngine:
             mod_count = np.empty(n_sites, dtype=np.int32)
         else:
             read_prob, site_prob, mod_count = out
-        with self._torch.cuda.device(self.device):
-            rc = self._lib.m6a_mil_infer_host_f32(
-                self._handle, _ptr(feats), _ptr(read_off), _ptr(kmer_idx), n_sites, site_id_base, n_samples, n_iters,
-                seed & 0xFFFFFFFFFFFFFFFF, read_threshold, _ptr(read_prob), _ptr(site_prob), _ptr(mod_count), n_chunks)
+        self._select()
+        rc = self._lib.m6a_mil_infer_host_f32(
+            self._handle, _ptr(feats), _ptr(read_off), _ptr(kmer_idx), n_sites, site_id_base, n_samples, n_iters,
+            seed & 0xFFFFFFFFFFFFFFFF, read_threshold, _ptr(read_prob), _ptr(site_prob), _ptr(mod_count), n_chunks)
         _cabi.check(rc, "m6a_mil_infer_host_f32")
         return read_prob, site_prob, mod_count
 

@@ -125,17 +125,20 @@ def plan_batches(n_reads: np.ndarray, lo: int, hi: int, reads_per_batch: int) ->
     return spans
 
 
-def _resolve_device(device: str, local_rank: int, world: int):
-    import torch
+def _resolve_device(device: str, local_rank: int, world: int) -> int:
+    """--device -> CUDA device index (no torch import: the single-GPU path only needs the C ABI)."""
+    from . import _cabi
     if str(device).startswith("cpu"):
         raise RuntimeError("m6anet_b200 runs the inference hot path only on CUDA devices (sm_100a); there is no CPU path. "
                            "Use --device cuda, or the reference implementation for CPU inference.")
-    if not torch.cuda.is_available():
+    n = _cabi.device_count()
+    if n < 1:
         raise RuntimeError("no CUDA device is visible; m6anet_b200 has no CPU fallback")
-    dev = torch.device(device)
-    if dev.index is None:
-        dev = torch.device("cuda", local_rank if world > 1 else torch.cuda.current_device())
-    return dev
+    text = str(device)
+    idx = _cabi.parse_device(device) if ":" in text or not isinstance(device, str) else (local_rank if world > 1 else 0)
+    if idx >= n:
+        raise RuntimeError(f"cuda:{idx} is not visible ({n} device(s))")
+    return idx
 
 
 def run_inference(model: MILModel, dl, args):
@@ -144,16 +147,16 @@ def run_inference(model: MILModel, dl, args):
     `dl` is the dataset itself or anything with a `.dataset` attribute (a DataLoader in the reference).
     Uses args.{out_dir, device, read_proba_threshold, num_iterations, n_processes, seed} like the reference.
     """
-    import torch
     ds = getattr(dl, "dataset", dl)
     rank, world, local_rank = env_world()
     dev = _resolve_device(args.device, local_rank, world)
-    torch.cuda.set_device(dev)
-    if world > 1:
+    if world > 1:     # torch only for the multi-GPU plumbing (torch.distributed over NCCL)
+        import torch
         import torch.distributed as dist
+        torch.cuda.set_device(dev)
         if not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group("nccl", device_id=dev)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     seed = int(getattr(args, "seed", 0))
     n_iters = int(args.num_iterations)
     thr = float(args.read_proba_threshold)
@@ -216,10 +219,9 @@ def run_inference(model: MILModel, dl, args):
             a, batch = item
             if errors:
                 continue
-            with torch.cuda.device(dev):
-                read_prob, site_prob, mod_count = eng.infer_host(batch.feats, batch.read_off, batch.kmer_idx, n_iters,
-                                                                 seed=seed, site_id_base=a, n_samples=N_SAMPLES,
-                                                                 read_threshold=thr)    # H2D -> kernel -> D2H
+            read_prob, site_prob, mod_count = eng.infer_host(batch.feats, batch.read_off, batch.kmer_idx, n_iters,
+                                                             seed=seed, site_id_base=a, n_samples=N_SAMPLES,
+                                                             read_threshold=thr)    # H2D -> kernel -> D2H
             all_sp.append(site_prob)
             all_mc.append(mod_count)
             q_out.put((batch, read_prob, site_prob, mod_count))
@@ -238,7 +240,8 @@ def run_inference(model: MILModel, dl, args):
 
     if world > 1:
         import torch.distributed as dist
-        sp_t, mc_t = all_gather_site_outputs(torch.from_numpy(site_prob).to(dev), torch.from_numpy(mod_count).to(dev), bounds)
+        tdev = torch.device("cuda", dev)
+        sp_t, mc_t = all_gather_site_outputs(torch.from_numpy(site_prob).to(tdev), torch.from_numpy(mod_count).to(tdev), bounds)
         site_prob, mod_count = sp_t.cpu().numpy(), mc_t.cpu().numpy()
         dist.barrier()
         if rank == 0:    # concatenate the shard files in site order behind the headers
