@@ -102,39 +102,80 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
+// One draw step of a lane's chain in the paired (n <= 256, two indices per word) or single regime.
+template <bool PAIRED>
+__device__ __forceinline__ void mc_step(uint32_t qaddr, uint32_t n, Mwc64x& g, float& prod, bool second_of_pair_wanted = true) {
+  if (PAIRED) {
+    uint32_t i1, i2;
+    g.next_pair(n, i1, i2);
+    prod *= lds_f32(qaddr + (i1 << 2));      // IMAD.WIDE, IMAD.HI, 2 x (LEA, LDS, FMUL) per word
+    if (second_of_pair_wanted) prod *= lds_f32(qaddr + (i2 << 2));
+  } else {
+    prod *= lds_f32(qaddr + (__umulhi(g.next(), n) << 2));   // IMAD.HI, LEA, LDS, FMUL
+  }
+}
+
+// rounds [k0, k1) of ONE chain, accumulated into v in round order (the canonical summation order)
+template <int NS, bool PAIRED>
+__device__ __forceinline__ void mc_rounds(uint32_t qaddr, uint32_t n, Mwc64x& g, int k0, int k1, float& v) {
+  constexpr int kSteps = PAIRED ? NS / 2 : NS;
+  for (int k = k0; k < k1; ++k) {
+    float prod = 1.0f;
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s) mc_step<PAIRED>(qaddr, n, g, prod);
+    if (PAIRED && (NS & 1)) mc_step<PAIRED>(qaddr, n, g, prod, false);
+    v += 1.0f - prod;
+  }
+}
+
+// rounds [0, kc) of TWO independent chains interleaved instruction by instruction: phase B is bound by the latency of
+// the serial MWC chain (wide multiply -> carry adds -> next multiply), and it has registers to spare
+template <int NS, bool PAIRED>
+__device__ __forceinline__ void mc_rounds_x2(uint32_t qa, uint32_t na, Mwc64x& ga, float& va, uint32_t qb, uint32_t nb,
+                                             Mwc64x& gb, float& vb, int kc) {
+  constexpr int kSteps = PAIRED ? NS / 2 : NS;
+  for (int k = 0; k < kc; ++k) {
+    float pa = 1.0f, pb = 1.0f;
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s) {
+      mc_step<PAIRED>(qa, na, ga, pa);
+      mc_step<PAIRED>(qb, nb, gb, pb);
+    }
+    if (PAIRED && (NS & 1)) {
+      mc_step<PAIRED>(qa, na, ga, pa, false);
+      mc_step<PAIRED>(qb, nb, gb, pb, false);
+    }
+    va += 1.0f - pa;
+    vb += 1.0f - pb;
+  }
+}
+
 template <int NS>
 __device__ __forceinline__ float mc_lane_smem(const float* __restrict__ qs, uint32_t n, Mwc64x& g, int rounds) {
   const uint32_t qaddr = smem_u32(qs);     // shared-space byte address of the site's q table
   float v = 0.0f;
-  if (n <= kPairedMaxReads) {              // warp-uniform: two indices per word
-    for (int k = 0; k < rounds; ++k) {
-      float prod = 1.0f;
-#pragma unroll
-      for (int s = 0; s < NS / 2; ++s) {
-        uint32_t i1, i2;
-        g.next_pair(n, i1, i2);
-        prod *= lds_f32(qaddr + (i1 << 2));  // IMAD.WIDE, IMAD.HI, 2 x (LEA, LDS, FMUL) per word
-        prod *= lds_f32(qaddr + (i2 << 2));
-      }
-      if (NS & 1) {
-        uint32_t i1, i2;
-        g.next_pair(n, i1, i2);
-        prod *= lds_f32(qaddr + (i1 << 2));
-      }
-      v += 1.0f - prod;
-    }
-  } else {
-    for (int k = 0; k < rounds; ++k) {
-      float prod = 1.0f;
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const uint32_t idx = __umulhi(g.next(), n);
-        prod *= lds_f32(qaddr + (idx << 2));   // IMAD.HI, LEA, LDS, FMUL
-      }
-      v += 1.0f - prod;
-    }
-  }
+  if (n <= kPairedMaxReads) mc_rounds<NS, true>(qaddr, n, g, 0, rounds, v);   // warp-uniform branch
+  else mc_rounds<NS, false>(qaddr, n, g, 0, rounds, v);
   return v;
+}
+
+// two (site, block) items of the same index regime at once; identical results to two mc_lane_smem calls
+template <int NS>
+__device__ __forceinline__ void mc_lane_smem_x2(const float* qsa, uint32_t na, Mwc64x& ga, int ra, float& va,
+                                                const float* qsb, uint32_t nb, Mwc64x& gb, int rb, float& vb) {
+  const uint32_t qa = smem_u32(qsa), qb = smem_u32(qsb);
+  const int kc = min(ra, rb);
+  va = 0.0f;
+  vb = 0.0f;
+  if (na <= kPairedMaxReads) {
+    mc_rounds_x2<NS, true>(qa, na, ga, va, qb, nb, gb, vb, kc);
+    mc_rounds<NS, true>(qa, na, ga, kc, ra, va);
+    mc_rounds<NS, true>(qb, nb, gb, kc, rb, vb);
+  } else {
+    mc_rounds_x2<NS, false>(qa, na, ga, va, qb, nb, gb, vb, kc);
+    mc_rounds<NS, false>(qa, na, ga, kc, ra, va);
+    mc_rounds<NS, false>(qb, nb, gb, kc, rb, vb);
+  }
 }
 
 // generic path: any n_samples, q from shared memory or 1 - read_prob from global, optional explicit indices
@@ -421,36 +462,76 @@ mil_infer_kernel(const KernelArgs a) {
 
     // ---- phase B: Monte-Carlo noisy-OR ----------------------------------------------------------
     {
-      // items (site, block) are dealt round-robin to the warps; (sl, blk) advance without a division
+      // items (site, block) are dealt round-robin to the warps, two at a time; (sl, blk) advance without a division
       const int items = ns * n_blocks;
-      int sl = 0, blk = warp;
-      while (blk >= n_blocks) { blk -= n_blocks; ++sl; }
-      for (int item = warp; item < items; item += kWarps) {
-        const int n = sm.roff[sl + 1] - sm.roff[sl];
+      auto advance = [&](int& sl_, int& blk_) {
+        blk_ += kWarps;
+        while (blk_ >= n_blocks) { blk_ -= n_blocks; ++sl_; }
+      };
+      // rounds of this lane in block blk: it = (blk*ipl + k)*32 + lane, k < ipl, it < n_iters
+      auto lane_rounds = [&](int blk_, long long& it0) {
+        it0 = static_cast<long long>(blk_) * ipl * 32 + lane;
+        const long long left = (static_cast<long long>(a.n_iters) - it0 + 31) / 32;
+        return static_cast<int>(left < 0 ? 0 : (left > ipl ? ipl : left));
+      };
+      auto run_single = [&](int sl_, int blk_) {
+        const int n = sm.roff[sl_ + 1] - sm.roff[sl_];
         float v = 0.0f;
         if (n > 0) {
-          // this lane's iterations: it = (blk*ipl + k)*32 + lane, k < ipl, it < n_iters
-          const long long it0 = static_cast<long long>(blk) * ipl * 32 + lane;
-          long long left = (static_cast<long long>(a.n_iters) - it0 + 31) / 32;   // rounds with it < n_iters
-          const int rounds = static_cast<int>(left < 0 ? 0 : (left > ipl ? ipl : left));
+          long long it0;
+          const int rounds = lane_rounds(blk_, it0);
           Mwc64x g;
-          g.seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk),
-                 static_cast<unsigned long long>(a.site_id_base + s0 + sl), a.seed);
+          g.seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk_),
+                 static_cast<unsigned long long>(a.site_id_base + s0 + sl_), a.seed);
           if (NS > 0 && q_in_smem && a.sample_idx == nullptr) {
-            v = mc_lane_smem<NS>(sm.q + sm.roff[sl], static_cast<uint32_t>(n), g, rounds);
+            v = mc_lane_smem<NS>(sm.q + sm.roff[sl_], static_cast<uint32_t>(n), g, rounds);
           } else {
-            const float* qbase = q_in_smem ? (sm.q + sm.roff[sl]) : (a.read_prob + r0 + sm.roff[sl]);
+            const float* qbase = q_in_smem ? (sm.q + sm.roff[sl_]) : (a.read_prob + r0 + sm.roff[sl_]);
             const uint16_t* ex = a.sample_idx != nullptr
-                                     ? a.sample_idx + (static_cast<size_t>(s0 + sl) * a.n_iters + it0) * a.n_samples
+                                     ? a.sample_idx + (static_cast<size_t>(s0 + sl_) * a.n_iters + it0) * a.n_samples
                                      : nullptr;
             v = mc_lane_generic(qbase, !q_in_smem, static_cast<uint32_t>(n), g, rounds, a.n_samples, ex,
                                 static_cast<size_t>(32) * a.n_samples);
           }
         }
         v = warp_butterfly_sum(v);
-        if (lane == 0) sm.partial[sl][blk] = v;
-        blk += kWarps;
-        while (blk >= n_blocks) { blk -= n_blocks; ++sl; }
+        if (lane == 0) sm.partial[sl_][blk_] = v;
+      };
+
+      int sl = 0, blk = warp;
+      while (blk >= n_blocks) { blk -= n_blocks; ++sl; }
+      for (int item = warp; item < items; item += 2 * kWarps) {
+        int sl2 = sl, blk2 = blk;
+        advance(sl2, blk2);
+        const bool have2 = item + kWarps < items;
+        const int na = sm.roff[sl + 1] - sm.roff[sl];
+        const int nb = have2 ? sm.roff[sl2 + 1] - sm.roff[sl2] : 0;
+        const bool fast2 = NS > 0 && q_in_smem && a.sample_idx == nullptr && have2 && na > 0 && nb > 0 &&
+                           ((na <= static_cast<int>(kPairedMaxReads)) == (nb <= static_cast<int>(kPairedMaxReads)));
+        if (fast2) {      // warp-uniform: two independent chains per lane, interleaved
+          long long it0a, it0b;
+          const int ra = lane_rounds(blk, it0a), rb = lane_rounds(blk2, it0b);
+          Mwc64x ga, gb;
+          ga.seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk),
+                  static_cast<unsigned long long>(a.site_id_base + s0 + sl), a.seed);
+          gb.seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk2),
+                  static_cast<unsigned long long>(a.site_id_base + s0 + sl2), a.seed);
+          float va, vb;
+          mc_lane_smem_x2<NS>(sm.q + sm.roff[sl], static_cast<uint32_t>(na), ga, ra, va, sm.q + sm.roff[sl2],
+                              static_cast<uint32_t>(nb), gb, rb, vb);
+          va = warp_butterfly_sum(va);
+          vb = warp_butterfly_sum(vb);
+          if (lane == 0) {
+            sm.partial[sl][blk] = va;
+            sm.partial[sl2][blk2] = vb;
+          }
+        } else {
+          run_single(sl, blk);
+          if (have2) run_single(sl2, blk2);
+        }
+        sl = sl2;
+        blk = blk2;
+        advance(sl, blk);
       }
     }
     __syncthreads();
