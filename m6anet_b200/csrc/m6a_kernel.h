@@ -8,7 +8,8 @@
 
 namespace m6a {
 
-// Tunables (overridable at build time for A/B experiments: make EXTRA="-DM6A_RPT=1 -DM6A_CTAS=3 ...")
+// Tunables (overridable at build time for A/B experiments: make EXTRA="-DM6A_PAIR_UNROLL=3 ..." OUT=...; the measured
+// alternatives are listed in profiles/r01_tile_size_ab.txt).  Rows per tile are chosen at run time (auto_tile_reads).
 #ifndef M6A_THREADS
 #define M6A_THREADS 256
 #endif
@@ -30,16 +31,12 @@ namespace m6a {
 #ifndef M6A_PAIR_UNROLL
 #define M6A_PAIR_UNROLL 5   // pair-loop unroll: deeper LDCU lookahead (1: 19.4 ms, 3: 18.36, 5: 18.35, 15: 17.8 but ragged 24.7)
 #endif
-#ifndef M6A_TILE_READS
-#define M6A_TILE_READS (M6A_THREADS * M6A_RPT)
-#endif
 constexpr int kPairUnroll = M6A_PAIR_UNROLL;
 constexpr int kThreads = M6A_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kReadsPerThread = M6A_RPT;
 constexpr int kCtasPerSm = M6A_CTAS;
 constexpr int kChunkReads = kThreads * kReadsPerThread;  // feature rows staged per bulk copy
-constexpr int kTileReads = M6A_TILE_READS;               // (legacy tunable; tiles are sized by auto_tile_reads in m6a_api.cu)
 constexpr int kSitesPerTileMax = M6A_GMAX;
 constexpr int kQCap = M6A_QCAP;         // q = 1-p entries kept in shared memory per tile
 constexpr int kCStride = kH1Max;        // even (float2 loads); 152 mod 32 = 24 keeps neighbouring site rows on distinct banks

@@ -23,7 +23,7 @@ import pathlib
 import shutil
 import warnings
 from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
-from typing import List, Optional
+from typing import List
 
 import numpy as np
 

@@ -22,7 +22,7 @@ from multiprocessing import Pool
 
 import numpy as np
 
-from .mil_oracle import ReadEncoderParams, read_probabilities
+from .mil_oracle import ReadEncoderParams
 
 
 def read_probabilities_torch(params: ReadEncoderParams, feats: np.ndarray, kmer_rows):

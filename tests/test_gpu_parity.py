@@ -236,7 +236,6 @@ def test_invalid_arguments_are_rejected(synthetic_inputs):
     with pytest.raises(M6AError):
         MilEngine(bad, "cuda:0")
     # the caller-owned workspace is validated: missing or too small -> M6A_EINVAL, nothing is launched
-    import ctypes as C
     import torch
     from m6anet_b200 import _cabi
     L = _cabi.lib()

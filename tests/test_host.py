@@ -1,14 +1,13 @@
 """CPU tests of the host-side mirror of the reference interface: registry, model-config plugin,
 dataset ingest (bit-exact against the reference's NanopolishDS output), CSV row formats, sharding."""
 import gzip
-import io
 import os
 import shutil
 
 import numpy as np
 import pytest
 
-from conftest import ASSETS, GOLDEN, MODEL_FILES
+from conftest import ASSETS, GOLDEN
 
 
 @pytest.fixture(scope="session")

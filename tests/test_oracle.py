@@ -1,7 +1,5 @@
 """Pins the CPU oracle (oracle/) to the reference: its golden files, outputs of the reference
 itself (tests/golden/make_golden.py) and Random123 known-answer vectors.  CPU only."""
-import gzip
-import io
 import os
 
 import numpy as np

@@ -3,7 +3,7 @@
 top stall sites.  Usage: ncu -i X.ncu-rep --page source --csv > src.csv; python tools/ncu_source_summary.py src.csv"""
 import csv
 import sys
-from collections import Counter, defaultdict
+from collections import Counter
 
 
 def main(path, top=25):
