@@ -115,6 +115,44 @@ def bundled():
     print("bundled:", len(ds), "sites", feats.shape[0], "reads")
 
 
+def make_replicate_dirs(src_dir, out_root):
+    """Two input directories for the replicate join: `a` = the bundled data, `b` = the same data.json with three
+    sites missing from data.info and the last ten rows moved to the front (exercises the outer join and its order).
+    Shared by this script and tests/test_host.py."""
+    import pandas as pd
+    dirs = []
+    for name in ("a", "b"):
+        d = os.path.join(out_root, name)
+        os.makedirs(d, exist_ok=True)
+        shutil.copyfile(os.path.join(src_dir, "data.json"), os.path.join(d, "data.json"))
+        dirs.append(d)
+    info = pd.read_csv(os.path.join(src_dir, "data.info"))
+    info.to_csv(os.path.join(dirs[0], "data.info"), index=False)
+    b = info.drop([0, 5, 7]).reset_index(drop=True)
+    b = pd.concat([b.iloc[-10:], b.iloc[:-10]]).reset_index(drop=True)
+    b.to_csv(os.path.join(dirs[1], "data.info"), index=False)
+    return dirs
+
+
+def replicates():
+    """Reference NanopolishReplicateDS (utils/data_utils.py:341-427) on the two directories above."""
+    import tempfile
+    from m6anet.utils.data_utils import NanopolishReplicateDS
+    src = os.path.join(REF, "m6anet", "tests", "data")
+    with tempfile.TemporaryDirectory() as tmp:
+        dirs = make_replicate_dirs(src, tmp)
+        ds = NanopolishReplicateDS(dirs, 20, PRETRAINED_CONFIGS["HCT116_RNA002"][2], mode="Inference")
+        pick = [0, 1, 3, len(ds) - 1]
+        items = [ds[i] for i in pick]
+        np.savez(os.path.join(HERE, "replicate_golden.npz"),
+                 tx_id=np.array(ds.data_info["transcript_id"]).astype(str), tx_pos=np.array(ds.data_info["transcript_position"], dtype=np.int64),
+                 n_reads=np.array(ds.data_info["n_reads"], dtype=np.int64), pick=np.array(pick),
+                 **{f"feats_{j}": it[0].numpy() for j, it in enumerate(items)},
+                 **{f"kmer_{j}": it[1].numpy()[0] for j, it in enumerate(items)},
+                 **{f"read_id_{j}": np.array([str(r) for r in it[4]]) for j, it in enumerate(items)})
+        print("replicates:", len(ds), "pooled sites")
+
+
 def synthetic_inputs():
     rng = np.random.default_rng(2024)
     centre = ["".join(c) for c in __import__("itertools").product("AGT", "GA", "A", "C", "ACT")]
@@ -158,6 +196,7 @@ def synthetic_outputs(tag, model, threshold, feats, read_off, kmer_idx, extra=No
 
 def main():
     bundled()
+    replicates()
     feats, read_off, kmer_idx = synthetic_inputs()
     for name, (_, thr, _) in PRETRAINED_CONFIGS.items():
         synthetic_outputs(name, ref_model(name), thr, feats, read_off, kmer_idx)

@@ -248,3 +248,28 @@ def test_native_ingest_reports_bad_input(tmp_path):
         bad = line.replace("GGGACTT", "GGGTCTT")
         (tmp_path / "data.json").write_text(bad)
         NanopolishDS(str(tmp_path), 20, C.DEFAULT_NORM_PATH).load_sites(0, 1)
+
+
+def test_replicate_join_matches_reference_order_and_content(bundled_dir, tmp_path):
+    """Site order, pooled read counts, features and "{id}_{rep}" read ids equal what the reference's
+    NanopolishReplicateDS produced for two directories with missing and reordered rows (fixture made by the reference)."""
+    import importlib.util
+    from m6anet_b200 import constants as C
+    from m6anet_b200.data import NanopolishReplicateDS
+    spec = importlib.util.spec_from_file_location("make_golden_dirs", os.path.join(GOLDEN, "make_golden.py"))
+    src = open(spec.origin).read()
+    ns = {"os": os, "shutil": shutil}
+    start = src.index("def make_replicate_dirs")
+    exec(src[start:src.index("def replicates()")], ns)          # only the pure directory builder, no reference import
+    dirs = ns["make_replicate_dirs"](bundled_dir, str(tmp_path))
+    g = np.load(os.path.join(GOLDEN, "replicate_golden.npz"))
+    ds = NanopolishReplicateDS(dirs, 20, C.DEFAULT_NORM_PATH)
+    assert list(ds._tx) == list(g["tx_id"]) and np.array_equal(ds._pos, g["tx_pos"]) and np.array_equal(ds.n_reads, g["n_reads"])
+    flat = ds.load_sites(0, len(ds))
+    for j, i in enumerate(g["pick"]):
+        feats, kmers, tx, pos, rid = ds[int(i)]
+        assert np.array_equal(feats, g[f"feats_{j}"]) and np.array_equal(kmers[0], g[f"kmer_{j}"])
+        assert [str(r) for r in rid] == list(g[f"read_id_{j}"])
+        sl = slice(flat.read_off[i], flat.read_off[i + 1])
+        assert np.array_equal(flat.feats[sl], g[f"feats_{j}"])
+        assert [f"{a}_{b}" for a, b in zip(flat.read_ids[sl], flat.read_rep[sl])] == list(g[f"read_id_{j}"])
