@@ -273,3 +273,38 @@ def test_replicate_join_matches_reference_order_and_content(bundled_dir, tmp_pat
         sl = slice(flat.read_off[i], flat.read_off[i + 1])
         assert np.array_equal(flat.feats[sl], g[f"feats_{j}"])
         assert [f"{a}_{b}" for a, b in zip(flat.read_ids[sl], flat.read_rep[sl])] == list(g[f"read_id_{j}"])
+
+
+def test_native_parser_number_formats_property(tmp_path):
+    """Property test: for arbitrary finite doubles written in any of Python's float spellings, the native parser
+    (std::from_chars) yields the same float32 features as json.loads + float64 normalisation."""
+    import json
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from m6anet_b200 import constants as C
+    from m6anet_b200.data import NanopolishDS
+
+    spell = [repr, lambda v: "%.17g" % v, lambda v: "%.6e" % v, lambda v: "%.3f" % v, lambda v: "%d" % int(v) if abs(v) < 1e15 else repr(v)]
+    finite = st.floats(min_value=-1e6, max_value=1e6, allow_nan=False, allow_infinity=False) | \
+        st.floats(min_value=-1e-300, max_value=1e-300, allow_nan=False) | st.sampled_from([0.0, -0.0, 5e-324, 1e22, 123456789.125])
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.lists(st.tuples(st.lists(finite, min_size=9, max_size=9), st.lists(st.integers(0, 4), min_size=9, max_size=9),
+                              st.integers(0, 10**9)), min_size=20, max_size=24))
+    def check(rows):
+        txt = []
+        for vals, how, rid in rows:
+            txt.append("[" + ",".join(spell[h](v) for v, h in zip(vals, how)) + "," + repr(float(rid)) + "]")
+        line = '{"tx":{"42":{"AGGACTG":[%s]}}}\n' % ",".join(txt)
+        parsed = json.loads(line)["tx"]["42"]["AGGACTG"]
+        (tmp_path / "data.json").write_text(line)
+        (tmp_path / "data.info").write_text(f"transcript_id,transcript_position,start,end,n_reads\ntx,42,0,{len(line)},{len(rows)}\n")
+        ds = NanopolishDS(str(tmp_path), 20, C.DEFAULT_NORM_PATH)
+        flat = ds.load_sites(0, 1, n_threads=1)
+        raw = np.array(parsed, dtype=np.float64)
+        mean, std = ds.get_norm_factor(["AGGAC", "GGACT", "GACTG"])
+        want = ((raw[:, :9] - mean) / std).astype(np.float32)
+        assert np.array_equal(flat.feats, want, equal_nan=True)
+        assert np.array_equal(flat.read_ids, raw[:, 9].astype(np.int64))
+        ds.close()
+
+    check()
