@@ -86,6 +86,8 @@ int m6a_model_destroy(m6a_model_t *model);
 /* Feature rows per tile of the device call, 64..4096; 0 (default) = automatic: a multiple of the site depth close to
  * 1000 rows (500 for small jobs).  Tiles are read-balanced: tile t holds the sites whose first row is in [t*T, (t+1)*T). */
 int m6a_model_set_tile_reads(m6a_model_t *model, int32_t tile_reads);
+/* The automatic choice for a job of n_sites sites / total_reads rows on a device with n_sms SMs (introspection). */
+int32_t m6a_auto_tile_reads(int64_t n_sites, int64_t total_reads, int32_t n_sms);
 
 /*
  * Score n_sites sites.  All data pointers are DEVICE pointers.

@@ -237,6 +237,10 @@ extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, c
                            workspace_bytes, stream);
 }
 
+extern "C" int32_t m6a_auto_tile_reads(int64_t n_sites, int64_t total_reads, int32_t n_sms) {
+  return auto_tile_reads(n_sites, total_reads, n_sms > 0 ? n_sms : 148);
+}
+
 extern "C" int64_t m6a_mil_workspace_bytes(int64_t total_reads) {
   if (total_reads < 0) return 0;
   return (total_reads / 64 + 2) * static_cast<int64_t>(sizeof(long long));   // tiles hold >= 64 rows

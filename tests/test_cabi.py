@@ -93,3 +93,16 @@ def test_sass_shows_the_blackwell_native_paths():
     assert re.search(r"LDCU\.64 UR\d+, c\[0x0\]\[UR\d+", sass)          # weights streamed from the parameter bank
     assert "HMMA" not in sass and "UTCHMMA" not in sass               # no tensor cores on this path (north_star)
     assert "LDL" not in sass.split("mil_infer_kernelILi20")[1].split("Function :")[0]   # no spills in the headline kernel
+
+
+def test_auto_tile_reads_policy(lib):
+    """Rows per tile: a multiple of the site depth near 1000 (constant depth), 1000 for uneven sites, ~500 for small jobs."""
+    t = lambda s, r: lib.m6a_auto_tile_reads(s, r, 148)
+    assert t(1_000_000, 50_000_000) == 1000            # headline job: 20 sites of 50 reads
+    assert t(1_000_000, 20_000_000) == 1000            # 50 sites of 20 reads (<= 64 sites per slice)
+    assert t(500_000, 15_000_000) == 990               # 33 sites of 30 reads
+    assert t(250_000, 20_000_000) == 960               # 12 pooled sites of 80 reads
+    assert t(125_000, 6_250_000) == 500                # one N=8 shard: smaller tiles, >= 48 tiles per CTA
+    assert t(1_000_000, 47_900_123) == 1000            # uneven sites
+    assert t(10, 7) == 500 and t(0, 0) >= 64
+    assert lib.m6a_mil_workspace_bytes(50_000_000) >= (50_000_000 // 500 + 2) * 8
