@@ -19,6 +19,7 @@
  *   m6a_sample_indices      np.random.choice index draw                     (:85)
  *   m6a_ingest_parts        NanopolishDS._load_data/__getitem__/get_norm_factor + inference_collate,
  *                            NanopolishReplicateDS.load_data                 utils/data_utils.py:152-248,395-427,498-506
+ *   m6a_info_count/_read    pd.read_csv(data.info)                          utils/data_utils.py:118-129
  *   m6a_write_site_csv      the site rows   '%s,%d,%s,%.16f,%s,%.16f'       utils/inference_utils.py:59-60
  *   m6a_write_indiv_csv     the read rows   '%s,%d,%s,%.16f'                utils/inference_utils.py:63-64
  *
@@ -172,6 +173,13 @@ int m6a_ingest_parts(const char *const *paths, int32_t n_files, const m6a_part_t
                      int32_t n_flank, const double *norm_mean, const double *norm_std,
                      const int32_t *kmer_id, float *feats, int64_t *read_ids, int32_t *kmer_idx,
                      int32_t n_threads, int64_t *bad_part);
+
+/* data.info reader (csv with a header naming transcript_id, transcript_position, start, end, n_reads; reference
+ * utils/data_utils.py:118-129 reads it with pandas).  m6a_info_count sizes the buffers, m6a_info_read fills them:
+ * tx_buf/tx_off = concatenated transcript ids + CSR offsets [n_rows+1]; the other columns as int64 [n_rows]. */
+int m6a_info_count(const char *path, int64_t *n_rows, int64_t *tx_bytes);
+int m6a_info_read(const char *path, int64_t n_rows, int64_t tx_bytes, char *tx_buf, int64_t *tx_off,
+                  int64_t *tx_pos, int64_t *start, int64_t *end, int64_t *n_reads);
 
 /* Appends the reference-format rows to the open file descriptor fd (rows are formatted by n_threads
  * workers and written in site order).  tx_buf/tx_off: concatenated transcript ids, CSR offsets [n_sites+1];

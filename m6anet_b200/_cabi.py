@@ -17,7 +17,8 @@ CSRC = os.path.join(_HERE, "csrc")
 EXPORTS = (
     "m6a_version", "m6a_strerror", "m6a_device_count", "m6a_set_device", "m6a_model_create", "m6a_model_destroy", "m6a_model_set_tile_reads", "m6a_auto_tile_reads", "m6a_mil_workspace_bytes",
     "m6a_mil_infer_f32",
-    "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_last_launch", "m6a_ingest_parts", "m6a_write_site_csv",
+    "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_last_launch", "m6a_ingest_parts", "m6a_info_count", "m6a_info_read",
+    "m6a_write_site_csv",
     "m6a_write_indiv_csv",
 )
 
@@ -96,6 +97,10 @@ def lib() -> C.CDLL:
     L.m6a_last_launch.argtypes = [C.POINTER(i32)] * 5
     L.m6a_ingest_parts.restype = C.c_int
     L.m6a_ingest_parts.argtypes = [C.POINTER(C.c_char_p), i32, vp, i64, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(i64)]
+    L.m6a_info_count.restype = C.c_int
+    L.m6a_info_count.argtypes = [C.c_char_p, C.POINTER(i64), C.POINTER(i64)]
+    L.m6a_info_read.restype = C.c_int
+    L.m6a_info_read.argtypes = [C.c_char_p, i64, i64, vp, vp, vp, vp, vp, vp]
     L.m6a_write_site_csv.restype = C.c_int
     L.m6a_write_site_csv.argtypes = [i32, i64, vp, vp, vp, vp, vp, vp, vp, i32]
     L.m6a_write_indiv_csv.restype = C.c_int

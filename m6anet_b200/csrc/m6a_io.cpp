@@ -240,6 +240,142 @@ extern "C" int m6a_ingest_parts(const char* const* paths, int32_t n_files, const
   return c.status.load();
 }
 
+// ---- data.info reader: csv with a header naming transcript_id,transcript_position,start,end,n_reads (any order,
+// extra columns ignored) -- reference utils/data_utils.py:118-129 (pd.read_csv) ---------------------------------------
+namespace {
+struct InfoFile {
+  std::vector<char> text;
+  int col[5] = {-1, -1, -1, -1, -1};   // column index of transcript_id, transcript_position, start, end, n_reads
+  size_t body = 0;                     // offset of the first data row
+};
+
+int load_info(const char* path, InfoFile& f) {
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return M6A_EIO;
+  const off_t size = lseek(fd, 0, SEEK_END);
+  if (size < 0) { close(fd); return M6A_EIO; }
+  f.text.resize(static_cast<size_t>(size));
+  size_t got = 0;
+  while (got < f.text.size()) {
+    const ssize_t r = pread(fd, f.text.data() + got, f.text.size() - got, static_cast<off_t>(got));
+    if (r <= 0) { close(fd); return M6A_EIO; }
+    got += static_cast<size_t>(r);
+  }
+  close(fd);
+  // header
+  const char* p = f.text.data();
+  const char* e = p + f.text.size();
+  const char* eol = static_cast<const char*>(memchr(p, '\n', e - p));
+  if (!eol) eol = e;
+  static const char* names[5] = {"transcript_id", "transcript_position", "start", "end", "n_reads"};
+  int c = 0;
+  const char* q = p;
+  while (q <= eol) {
+    const char* comma = static_cast<const char*>(memchr(q, ',', eol - q));
+    const char* stop = comma ? comma : eol;
+    size_t len = static_cast<size_t>(stop - q);
+    if (len && q[len - 1] == '\r') --len;
+    for (int k = 0; k < 5; ++k)
+      if (strlen(names[k]) == len && !strncmp(q, names[k], len)) f.col[k] = c;
+    ++c;
+    if (!comma) break;
+    q = comma + 1;
+  }
+  for (int k = 0; k < 5; ++k)
+    if (f.col[k] < 0) return M6A_EPARSE;
+  f.body = static_cast<size_t>(eol - p) + (eol < e ? 1 : 0);
+  return M6A_OK;
+}
+}  // namespace
+
+// Counts the data rows and the total bytes of the transcript ids (to size the buffers of m6a_info_read).
+extern "C" int m6a_info_count(const char* path, int64_t* n_rows, int64_t* tx_bytes) {
+  if (!path || !n_rows || !tx_bytes) return M6A_EINVAL;
+  InfoFile f;
+  const int rc = load_info(path, f);
+  if (rc != M6A_OK) return rc;
+  int64_t rows = 0, bytes = 0;
+  const char* p = f.text.data() + f.body;
+  const char* e = f.text.data() + f.text.size();
+  while (p < e) {
+    const char* eol = static_cast<const char*>(memchr(p, '\n', e - p));
+    if (!eol) eol = e;
+    if (eol > p && !(eol - p == 1 && *p == '\r')) {
+      // length of field col[0]
+      const char* q = p;
+      for (int c = 0; c < f.col[0]; ++c) {
+        q = static_cast<const char*>(memchr(q, ',', eol - q));
+        if (!q) return M6A_EPARSE;
+        ++q;
+      }
+      const char* stop = static_cast<const char*>(memchr(q, ',', eol - q));
+      if (!stop) stop = eol;
+      bytes += stop - q;
+      ++rows;
+    }
+    p = eol + 1;
+  }
+  *n_rows = rows;
+  *tx_bytes = bytes;
+  return M6A_OK;
+}
+
+// Fills tx_buf/tx_off (concatenated transcript ids, CSR offsets [n_rows+1]) and the four integer columns.
+extern "C" int m6a_info_read(const char* path, int64_t n_rows, int64_t tx_bytes, char* tx_buf, int64_t* tx_off,
+                             int64_t* tx_pos, int64_t* start, int64_t* end, int64_t* n_reads) {
+  if (!path || n_rows < 0 || !tx_off || (n_rows > 0 && (!tx_buf || !tx_pos || !start || !end || !n_reads))) return M6A_EINVAL;
+  InfoFile f;
+  const int rc = load_info(path, f);
+  if (rc != M6A_OK) return rc;
+  int64_t* dst[5] = {nullptr, tx_pos, start, end, n_reads};
+  int64_t row = 0, used = 0;
+  tx_off[0] = 0;
+  const char* p = f.text.data() + f.body;
+  const char* e = f.text.data() + f.text.size();
+  while (p < e) {
+    const char* eol = static_cast<const char*>(memchr(p, '\n', e - p));
+    if (!eol) eol = e;
+    if (eol > p && !(eol - p == 1 && *p == '\r')) {
+      if (row >= n_rows) return M6A_EPARSE;
+      const char* q = p;
+      int c = 0, seen = 0;
+      while (q <= eol) {
+        const char* comma = static_cast<const char*>(memchr(q, ',', eol - q));
+        const char* stop = comma ? comma : eol;
+        for (int k = 0; k < 5; ++k) {
+          if (f.col[k] != c) continue;
+          ++seen;
+          if (k == 0) {
+            const int64_t len = stop - q;
+            if (used + len > tx_bytes) return M6A_EPARSE;
+            memcpy(tx_buf + used, q, static_cast<size_t>(len));
+            used += len;
+            tx_off[row + 1] = used;
+          } else {
+            int64_t v = 0;
+            const char* stop2 = (stop > q && stop[-1] == '\r') ? stop - 1 : stop;
+            auto res = std::from_chars(q, stop2, v);
+            if (res.ec != std::errc()) {         // pandas may have written a float ("12.0"): accept integral doubles
+              double dv;
+              auto r2 = std::from_chars(q, stop2, dv);
+              if (r2.ec != std::errc()) return M6A_EPARSE;
+              v = static_cast<int64_t>(dv);
+            }
+            dst[k][row] = v;
+          }
+        }
+        ++c;
+        if (!comma) break;
+        q = comma + 1;
+      }
+      if (seen != 5) return M6A_EPARSE;
+      ++row;
+    }
+    p = eol + 1;
+  }
+  return row == n_rows ? M6A_OK : M6A_EPARSE;
+}
+
 // '%s,%d,%s,%.16f,%s,%.16f\n' % (tx_id, tx_pos, n_read, site_prob, kmer, mod_ratio)   utils/inference_utils.py:59-60
 extern "C" int m6a_write_site_csv(int32_t fd, int64_t n_sites, const char* tx_buf, const int64_t* tx_off,
                                   const int64_t* tx_pos, const int64_t* read_off, const float* site_prob,

@@ -51,16 +51,38 @@ def load_norm_factors(norm_path: str) -> Dict[str, Tuple[np.ndarray, np.ndarray]
     """5-mer -> (mean[3], std[3]) float64, order (dwell, sd, mean).  Accepts this package's .npz or a
     reference .joblib (reference utils/data_utils.py:79-80)."""
     if str(norm_path).endswith(".npz"):
-        z = np.load(norm_path)
-        return {str(k): (z["mean"][i], z["std"][i]) for i, k in enumerate(z["kmers"])}
+        with np.load(norm_path) as z:
+            kmers, mean, std = z["kmers"], z["mean"], z["std"]      # read each array once (NpzFile re-reads per access)
+        return {str(k): (mean[i], std[i]) for i, k in enumerate(kmers)}
     import joblib
     nd = joblib.load(norm_path)
     return {str(k): (np.asarray(v[0], dtype=np.float64), np.asarray(v[1], dtype=np.float64)) for k, v in nd.items()}
 
 
-def _read_info(root_dir: str):
-    import pandas as pd
-    return pd.read_csv(os.path.join(root_dir, "data.info"))
+def read_info(root_dir: str):
+    """data.info -> (transcript_id bytes array 'S<w>', transcript_position, start, end, n_reads) int64 arrays.
+    Native reader (m6a_info_count / m6a_info_read); the reference uses pd.read_csv (utils/data_utils.py:118-129)."""
+    import ctypes as C
+    from . import _cabi
+    L = _cabi.lib()
+    path = os.fsencode(os.path.join(root_dir, "data.info"))
+    n, nb = C.c_int64(0), C.c_int64(0)
+    _cabi.check(L.m6a_info_count(path, C.byref(n), C.byref(nb)), f"m6a_info_count({os.fsdecode(path)})")
+    n, nb = int(n.value), int(nb.value)
+    buf = np.zeros(max(nb, 1), dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.int64)
+    cols = [np.zeros(max(n, 1), dtype=np.int64) for _ in range(4)]
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _cabi.check(L.m6a_info_read(path, n, nb, vp(buf), vp(off), *[vp(c) for c in cols]), f"m6a_info_read({os.fsdecode(path)})")
+    # variable-length ids -> fixed-width bytes array (vectorised scatter into a zero-padded [n, width] matrix)
+    lengths = np.diff(off)
+    width = int(lengths.max()) if n else 1
+    mat = np.zeros((n, max(width, 1)), dtype=np.uint8)
+    if nb:
+        rows = np.repeat(np.arange(n), lengths)
+        mat[rows, np.arange(nb) - np.repeat(off[:-1], lengths)] = buf[:nb]
+    tx = mat.view(f"S{max(width, 1)}").reshape(n)
+    return tx, cols[0][:n], cols[1][:n], cols[2][:n], cols[3][:n]
 
 
 class NanopolishDS:
@@ -91,25 +113,36 @@ class NanopolishDS:
 
     # ---- index ------------------------------------------------------------------------------------
     def initialize_data_info(self):
-        info = _read_info(self.root_dir)
+        tx, pos, start, end, n_reads = read_info(self.root_dir)
         self.data_fpath = os.path.join(self.root_dir, "data.json")
-        self.data_info = info[info["n_reads"] >= self.min_reads].reset_index(drop=True)     # data_utils.py:129
-        self._tx = self.data_info["transcript_id"].to_numpy().astype(str)
-        self._pos = self.data_info["transcript_position"].to_numpy(dtype=np.int64)
-        self._n_reads = self.data_info["n_reads"].to_numpy(dtype=np.int64)
+        keep = n_reads >= self.min_reads                                                   # data_utils.py:129
+        self._tx_bytes = tx[keep]
+        self._pos = pos[keep]
+        self._n_reads = n_reads[keep]
         # part tables (one part per site here): CSR pointer over sites + per-part file / byte range / replicate / rows
-        S = len(self._tx)
+        S = len(self._pos)
         self._paths = [self.data_fpath]
         self._part_ptr = np.arange(S + 1, dtype=np.int64)
         self._part_file = np.zeros(S, dtype=np.int32)
         self._part_rep = np.zeros(S, dtype=np.int32)
-        self._part_start = self.data_info["start"].to_numpy(dtype=np.int64)
-        self._part_end = self.data_info["end"].to_numpy(dtype=np.int64)
+        self._part_start = start[keep]
+        self._part_end = end[keep]
         self._part_rows = self._n_reads.copy()
         self._multi = False
 
+    @property
+    def _tx(self) -> np.ndarray:
+        """transcript ids as a str array (decoded on demand; the index keeps them as fixed-width bytes)"""
+        return self._tx_bytes.astype(str)
+
+    @property
+    def data_info(self):
+        """pandas view of the site index (reference attribute name); built on demand"""
+        import pandas as pd
+        return pd.DataFrame({"transcript_id": self._tx, "transcript_position": self._pos, "n_reads": self._n_reads})
+
     def __len__(self) -> int:
-        return len(self._tx)
+        return len(self._pos)
 
     @property
     def n_reads(self) -> np.ndarray:
@@ -128,7 +161,7 @@ class NanopolishDS:
         if len(self) == 0:
             return self.num_neighboring_features
         path, s, e, _ = self._site_parts(0)[0]
-        kmer, _ = self._load_data(path, self._tx[0], int(self._pos[0]), s, e)
+        kmer, _ = self._load_data(path, self._tx_bytes[0].decode(), int(self._pos[0]), s, e)
         return (len(kmer) - 5) // 2
 
     def _site_parts(self, idx: int):
@@ -159,15 +192,16 @@ class NanopolishDS:
     def load_data(self, idx: int):
         """(tx_id, tx_pos, read_ids, raw selected features float64 [n, 9], sequence)."""
         feats, ids, seq = [], [], None
+        tx_id = self._tx_bytes[idx].decode()
         for path, s, e, rep in self._site_parts(idx):
-            kmer, arr = self._load_data(path, self._tx[idx], int(self._pos[idx]), s, e)
+            kmer, arr = self._load_data(path, tx_id, int(self._pos[idx]), s, e)
             if seq is None:
                 seq = kmer
             else:
                 assert seq == kmer
             feats.append(arr[:, self.indices])
             ids.append(self._read_id_array(arr[:, -1], rep))
-        return self._tx[idx], int(self._pos[idx]), np.concatenate(ids), np.concatenate(feats), seq
+        return tx_id, int(self._pos[idx]), np.concatenate(ids), np.concatenate(feats), seq
 
     def _retrieve_full_sequence(self, kmer: str, n_neighboring_features: int = 1) -> str:
         # centre 5-mer plus n flanks out of a (5 + 2T)-mer.  (The reference's slice at data_utils.py:262 returns a
@@ -253,14 +287,15 @@ class NanopolishDS:
             if bad.value >= 0:
                 i = a + bad.value
                 site = lo + int(parts["site"][bad.value])
-                where = (f" (site {self._tx[site]}:{self._pos[site]}, file {self._paths[self._part_file[i]]}, bytes "
+                where = (f" (site {self._tx_bytes[site].decode()}:{self._pos[site]}, file {self._paths[self._part_file[i]]}, bytes "
                          f"[{self._part_start[i]}, {self._part_end[i]}))")
             raise _cabi.M6AError(rc, "m6a_ingest_parts" + where)
         read_off = np.zeros(S + 1, dtype=np.int64)
         read_off[1:] = row_off[1:][np.cumsum(counts) - 1] if S and (b - a) else 0
         centre = np.array([self.int_to_kmer[int(k)] for k in kmer_idx[:, n_pos // 2]]) if S else np.array([], dtype=str)
         rep = np.repeat(self._part_rep[a:b], rows).astype(np.int32) if self._multi else None
-        return SiteBatch(feats=feats, read_off=read_off, kmer_idx=kmer_idx, read_ids=read_ids, tx_ids=self._tx[lo:hi],
+        return SiteBatch(feats=feats, read_off=read_off, kmer_idx=kmer_idx, read_ids=read_ids,
+                         tx_ids=self._tx_bytes[lo:hi].astype(str),
                          tx_pos=self._pos[lo:hi], kmers=centre, read_rep=rep)
 
     def close(self):
@@ -284,36 +319,37 @@ class NanopolishReplicateDS(NanopolishDS):
         super().__init__(list(root_dir), min_reads, norm_path, num_neighboring_features, mode, n_processes)
 
     def initialize_data_info(self):
-        import pandas as pd
-        keys = ["transcript_id", "transcript_position"]
-        frames = []
-        for rep, d in enumerate(self.root_dir):
-            df = _read_info(d)
-            df["rep"] = rep
-            frames.append(df)
-        allrows = pd.concat(frames, ignore_index=True)
-        site_key = allrows[keys].drop_duplicates(keep="first").reset_index(drop=True)      # outer join, first-appearance order
-        site_key["site"] = np.arange(len(site_key))
-        allrows = allrows.merge(site_key, on=keys, how="left", sort=False)
-        total = allrows.groupby("site", sort=True)["n_reads"].sum().to_numpy()
+        # outer join of the directories on (transcript_id, transcript_position), sites in first-appearance order
+        cols = [read_info(d) for d in self.root_dir]
+        width = max(c[0].dtype.itemsize for c in cols)
+        tx = np.concatenate([c[0].astype(f"S{width}") for c in cols])
+        pos, start, end, n_reads = (np.concatenate([c[k] for c in cols]) for k in (1, 2, 3, 4))
+        rep = np.concatenate([np.full(len(c[1]), r, dtype=np.int32) for r, c in enumerate(cols)])
+        key = np.rec.fromarrays([tx, pos], names="tx,pos")
+        uniq, first, inverse = np.unique(key, return_index=True, return_inverse=True)
+        order = np.argsort(first, kind="stable")                 # unique keys by first appearance
+        rank = np.empty(len(uniq), dtype=np.int64)
+        rank[order] = np.arange(len(uniq))
+        site = rank[inverse.reshape(-1)]
+        total = np.bincount(site, weights=n_reads, minlength=len(uniq)).astype(np.int64)
         keep = total >= self.min_reads                                                   # data_utils.py:373
         new_id = np.cumsum(keep) - 1
-        self._tx = site_key["transcript_id"].to_numpy().astype(str)[keep]
-        self._pos = site_key["transcript_position"].to_numpy(dtype=np.int64)[keep]
-        self._n_reads = total[keep].astype(np.int64)
-        rows = allrows[keep[allrows["site"].to_numpy()]].sort_values(["site", "rep"], kind="stable")
-        site_new = new_id[rows["site"].to_numpy()]
+        self._tx_bytes = uniq["tx"][order][keep]
+        self._pos = uniq["pos"][order][keep].astype(np.int64)
+        self._n_reads = total[keep]
+        rows = np.nonzero(keep[site])[0]
+        rows = rows[np.lexsort((rep[rows], site[rows]))]         # by site, then directory
+        site_new = new_id[site[rows]]
         self._paths = [os.path.join(d, "data.json") for d in self.root_dir]
-        self._part_file = rows["rep"].to_numpy(dtype=np.int32)
-        self._part_rep = rows["rep"].to_numpy(dtype=np.int32)
-        self._part_start = rows["start"].to_numpy(dtype=np.int64)
-        self._part_end = rows["end"].to_numpy(dtype=np.int64)
-        self._part_rows = rows["n_reads"].to_numpy(dtype=np.int64)
+        self._part_file = rep[rows].astype(np.int32)
+        self._part_rep = rep[rows].astype(np.int32)
+        self._part_start = start[rows]
+        self._part_end = end[rows]
+        self._part_rows = n_reads[rows]
         self._part_ptr = np.zeros(int(keep.sum()) + 1, dtype=np.int64)
         np.cumsum(np.bincount(site_new, minlength=int(keep.sum())), out=self._part_ptr[1:])
         self._multi = True
-        self.data_info = pd.DataFrame({"transcript_id": self._tx, "transcript_position": self._pos, "n_reads": self._n_reads})
-        self.fpath_mapping = {d: rep for rep, d in enumerate(self.root_dir)}
+        self.fpath_mapping = {d: rep_ for rep_, d in enumerate(self.root_dir)}
         self.data_fpath = None
 
     def _read_id_array(self, raw: np.ndarray, rep: int):

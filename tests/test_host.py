@@ -308,3 +308,28 @@ def test_native_parser_number_formats_property(tmp_path):
         ds.close()
 
     check()
+
+
+def test_native_info_reader_matches_pandas(bundled_dir, tmp_path):
+    import pandas as pd
+    from m6anet_b200._cabi import M6AError
+    from m6anet_b200.data import read_info
+    want = pd.read_csv(os.path.join(bundled_dir, "data.info"))
+    tx, pos, start, end, n = read_info(bundled_dir)
+    assert list(tx.astype(str)) == list(want["transcript_id"]) and np.array_equal(pos, want["transcript_position"])
+    assert np.array_equal(start, want["start"]) and np.array_equal(end, want["end"]) and np.array_equal(n, want["n_reads"])
+    # column order from the header, extra columns, CRLF, float-formatted integers, no trailing newline
+    d = tmp_path / "odd"
+    d.mkdir()
+    (d / "data.info").write_text("n_reads,extra,end,transcript_id,start,transcript_position\r\n"
+                                 "25,x,120,ENST0001.1,0,17\r\n20.0,y,260,T2,120,3\r\n\r\n7,z,300,a_very_long_transcript_name.12,260,99")
+    tx, pos, start, end, n = read_info(str(d))
+    assert list(tx.astype(str)) == ["ENST0001.1", "T2", "a_very_long_transcript_name.12"]
+    assert list(pos) == [17, 3, 99] and list(start) == [0, 120, 260] and list(end) == [120, 260, 300] and list(n) == [25, 20, 7]
+    (d / "data.info").write_text("transcript_id,transcript_position,start,end\nt,1,0,5\n")
+    with pytest.raises(M6AError):
+        read_info(str(d))
+    (d / "data.info").write_text("transcript_id,transcript_position,start,end,n_reads\n")
+    assert len(read_info(str(d))[0]) == 0
+    with pytest.raises(M6AError):
+        read_info(str(tmp_path / "missing"))
