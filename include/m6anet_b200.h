@@ -17,6 +17,11 @@
  *                              calculate_site_proba/_calculate_site_proba   (:54,74-104)
  *   m6a_mil_infer_host_f32  the same, including features.to(device) / probs.cpu()  (:35-36,41)
  *   m6a_sample_indices      np.random.choice index draw                     (:85)
+ *   m6a_mil_validate_f32    the evaluation loop of validate(): per pass one bag of min_reads reads per site drawn
+ *   m6a_mil_validate_host_f32   WITHOUT replacement (utils/data_utils.py:213-214), MILModel.forward on it
+ *                            (model/model.py:155-164: read encoder + pooling block, model_blocks/pooling_blocks.py:96-98,
+ *                            127-129,158-160), passes averaged             utils/training_utils.py:236-256
+ *   m6a_sample_bags         np.random.choice(n, min_reads, replace=False)   utils/data_utils.py:214
  *   m6a_ingest_parts        NanopolishDS._load_data/__getitem__/get_norm_factor + inference_collate,
  *                            NanopolishReplicateDS.load_data                 utils/data_utils.py:152-248,395-427,498-506
  *   m6a_info_count/_read    pd.read_csv(data.info)                          utils/data_utils.py:118-129
@@ -53,6 +58,12 @@ extern "C" {
 #define M6A_H2 32            /* width of the second Linear block                            */
 #define M6A_H1_MAX 152       /* max width of the first Linear block (shipped models: 150)   */
 #define M6A_MAX_READS_EXPLICIT 65535 /* uint16 explicit indices                             */
+#define M6A_MAX_SAMPLES 64   /* reads per bag limit (n_samples)                             */
+
+/* Pooling block of the model, used by the validate()-style entry points (reference model_blocks/pooling_blocks.py). */
+#define M6A_POOL_PROD 0      /* SigmoidProdPooling  1 - prod(1 - p)   :127-129              */
+#define M6A_POOL_MEAN 1      /* SigmoidMeanPooling  mean(p)           :96-98                */
+#define M6A_POOL_MAX 2       /* SigmoidMaxPooling   max(p)            :158-160              */
 
 /*
  * Read-encoder parameters, HOST pointers, row-major float32, eval-mode BatchNorm already folded
@@ -100,7 +111,7 @@ int32_t m6a_auto_tile_reads(int64_t n_sites, int64_t total_reads, int32_t n_sms)
  *   kmer_idx    [n_sites, 3] int32 five-mer ids of the site's 7-mer (ignored when emb_dim == 0; may be NULL then)
  *   site_id_base  global id of site 0: the RNG counter is (site_id_base + s), so results do not
  *               depend on how sites are sharded over GPUs
- *   n_samples   reads per bag (the reference hard-codes 20), 1..64
+ *   n_samples   reads per bag (the reference hard-codes 20), 1..M6A_MAX_SAMPLES
  *   n_iters     Monte-Carlo iterations (>= 1)
  *   seed        Philox key of the index streams
  *   sample_idx  optional [n_sites, n_iters, n_samples] uint16 explicit indices (parity / replay
@@ -138,6 +149,39 @@ int m6a_mil_infer_host_f32(const m6a_model_t *model, const float *feats, const i
                            const int32_t *kmer_idx, int64_t n_sites, int64_t site_id_base,
                            int32_t n_samples, int32_t n_iters, uint64_t seed, float read_threshold,
                            float *read_prob, float *site_prob, int32_t *mod_count, int32_t n_chunks);
+
+/*
+ * validate()-style literal MIL forward: the evaluation loop of the reference (utils/training_utils.py:236-256) for a
+ * batch of sites.  The read encoder runs once per read (eval mode: a read's probability does not depend on its bag);
+ * then every pass `it` < n_iters pools ONE bag of n_samples reads per site with the model's pooling block.
+ * Arguments as m6a_mil_infer_f32, plus
+ *   pooling     M6A_POOL_PROD / _MEAN / _MAX
+ *   replace     0: bags WITHOUT replacement, like np.random.choice(n, min_reads, replace=False) of the reference's
+ *               evaluation datasets (utils/data_utils.py:214) -- Floyd's algorithm on the (site, block, lane) MWC64X
+ *               streams, one word per pick (specification: oracle/philox.py "Floyd bags"); a site with fewer than
+ *               n_samples reads has no bag: its outputs are NaN.  1: the inference index stream (with replacement).
+ *   sample_idx  optional explicit bags [n_sites, n_iters, n_samples] uint16 (replays the reference's MT19937 draw);
+ *               overrides `replace`
+ * outputs
+ *   bag_prob    [n_sites, n_iters] float32 pooled probability of every pass (validate()'s y_pred, transposed); may be NULL
+ *   site_prob   [n_sites] float32 mean over the passes (device summation order; the host mirror re-averages bag_prob in
+ *               pass order like np.mean(all_y_pred, axis=0))
+ *   read_prob, mod_count  as m6a_mil_infer_f32
+ */
+int m6a_mil_validate_f32(const m6a_model_t *model, const float *feats, const int64_t *read_off,
+                         const int32_t *kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
+                         int32_t n_samples, int32_t n_iters, uint64_t seed, const uint16_t *sample_idx,
+                         int32_t pooling, int32_t replace, float read_threshold, float *read_prob, float *bag_prob,
+                         float *site_prob, int32_t *mod_count, void *workspace, int64_t workspace_bytes, void *stream);
+/* The same with HOST buffers, through the chunked H2D / kernel / D2H pipeline of m6a_mil_infer_host_f32. */
+int m6a_mil_validate_host_f32(const m6a_model_t *model, const float *feats, const int64_t *read_off,
+                              const int32_t *kmer_idx, int64_t n_sites, int64_t site_id_base, int32_t n_samples,
+                              int32_t n_iters, uint64_t seed, int32_t pooling, int32_t replace, float read_threshold,
+                              float *read_prob, float *bag_prob, float *site_prob, int32_t *mod_count, int32_t n_chunks);
+/* Writes the device without-replacement bags of one site: out [n_iters, n_samples] int32 (DEVICE pointer), distinct
+ * inside a bag.  Test hook like m6a_sample_indices; M6A_ERANGE when n_reads < n_samples. */
+int m6a_sample_bags(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters, int32_t n_samples,
+                    int32_t *out, void *stream);
 
 /* Writes the device index stream of one site: out [n_iters, n_samples] int32 (DEVICE pointer).
  * Test hook proving the device generator equals oracle/philox.py bit for bit. */

@@ -17,7 +17,8 @@ CSRC = os.path.join(_HERE, "csrc")
 EXPORTS = (
     "m6a_version", "m6a_strerror", "m6a_device_count", "m6a_set_device", "m6a_model_create", "m6a_model_destroy", "m6a_model_set_tile_reads", "m6a_auto_tile_reads", "m6a_mil_workspace_bytes",
     "m6a_mil_infer_f32",
-    "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_last_launch", "m6a_ingest_parts", "m6a_info_count", "m6a_info_read",
+    "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_mil_validate_f32", "m6a_mil_validate_host_f32", "m6a_sample_bags",
+    "m6a_last_launch", "m6a_ingest_parts", "m6a_info_count", "m6a_info_read",
     "m6a_write_site_csv",
     "m6a_write_indiv_csv",
 )
@@ -93,6 +94,13 @@ def lib() -> C.CDLL:
     L.m6a_mil_infer_host_f32.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, u64, f32, vp, vp, vp, i32]
     L.m6a_sample_indices.restype = C.c_int
     L.m6a_sample_indices.argtypes = [u64, i64, i32, i32, i32, vp, vp]
+    L.m6a_mil_validate_f32.restype = C.c_int
+    L.m6a_mil_validate_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, u64, vp, i32, i32, f32, vp, vp, vp, vp, vp,
+                                       i64, vp]
+    L.m6a_mil_validate_host_f32.restype = C.c_int
+    L.m6a_mil_validate_host_f32.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, u64, i32, i32, f32, vp, vp, vp, vp, i32]
+    L.m6a_sample_bags.restype = C.c_int
+    L.m6a_sample_bags.argtypes = [u64, i64, i32, i32, i32, vp, vp]
     L.m6a_last_launch.restype = C.c_int
     L.m6a_last_launch.argtypes = [C.POINTER(i32)] * 5
     L.m6a_ingest_parts.restype = C.c_int

@@ -13,12 +13,17 @@
 
 using namespace m6a;
 
+static_assert(M6A_MAX_SAMPLES == kMaxSamples && M6A_POOL_PROD == kPoolProd && M6A_POOL_MEAN == kPoolMean &&
+                  M6A_POOL_MAX == kPoolMax && M6A_N_SIG == kNSig && M6A_H2 == kH2 && M6A_H1_MAX == kH1Max,
+              "include/m6anet_b200.h and the kernel limits disagree");
+
 extern "C" int64_t m6a_mil_workspace_bytes(int64_t total_reads);
 constexpr int kHostSlots = 3;
 struct HostSlot {   // one stage of the host-buffer pipeline (m6a_mil_infer_host_f32)
   cudaStream_t stream = nullptr;
   void *d_feats = nullptr, *d_off = nullptr, *d_kmer = nullptr, *d_rp = nullptr, *d_sp = nullptr, *d_mc = nullptr, *d_ws = nullptr;
-  size_t cap_feats = 0, cap_off = 0, cap_kmer = 0, cap_rp = 0, cap_sp = 0, cap_mc = 0, cap_ws = 0;
+  void* d_bag = nullptr;      // per-pass bag probabilities (m6a_mil_validate_host_f32 only)
+  size_t cap_feats = 0, cap_off = 0, cap_kmer = 0, cap_rp = 0, cap_sp = 0, cap_mc = 0, cap_ws = 0, cap_bag = 0;
   int64_t* h_off = nullptr;   // pinned staging for re-based offsets
   size_t cap_hoff = 0;
 };
@@ -178,9 +183,10 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
                              const int32_t* kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
                              int32_t n_samples, int32_t n_iters, uint64_t seed, const uint16_t* sample_idx,
                              float read_threshold, float* read_prob, float* site_prob, int32_t* mod_count,
-                             void* workspace, int64_t workspace_bytes, void* stream) {
+                             void* workspace, int64_t workspace_bytes, void* stream, const BagArgs* bags = nullptr) {
   if (!model || n_sites < 0 || total_reads < 0) return M6A_EINVAL;
-  if (n_samples < 1 || n_samples > 64 || n_iters < 1) return M6A_EINVAL;
+  if (n_samples < 1 || n_samples > kMaxSamples || n_iters < 1) return M6A_EINVAL;
+  if (bags && (bags->pool < kPoolProd || bags->pool > kPoolMax || (bags->replace != 0 && bags->replace != 1))) return M6A_EINVAL;
   if (n_sites == 0) return M6A_OK;
   if (!read_off || !site_prob || !mod_count) return M6A_EINVAL;
   if (total_reads > 0 && (!feats || !read_prob)) return M6A_EINVAL;
@@ -219,7 +225,7 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
 
   LaunchInfo info;
   cudaError_t e = launch_tile_bounds(read_off, n_sites, a.n_tiles, tile_reads, d_bounds, st);
-  if (e == cudaSuccess) e = launch_mil_infer(a, &model->host_image, model->n_sms, st, &info);
+  if (e == cudaSuccess) e = launch_mil_infer(a, &model->host_image, bags, model->n_sms, st, &info);
   if (e != cudaSuccess) return static_cast<int>(e);
   g_last = info;
   g_last_launches = 2;   // tile_bounds_kernel + mil_infer_kernel
@@ -237,6 +243,21 @@ extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, c
                            workspace_bytes, stream);
 }
 
+// validate()-style literal MIL forward (reference utils/training_utils.py:213-268): same read encoder, phase B pools one
+// bag per (site, pass) instead of the Monte-Carlo noisy-OR
+extern "C" int m6a_mil_validate_f32(const m6a_model_t* model, const float* feats, const int64_t* read_off,
+                                    const int32_t* kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
+                                    int32_t n_samples, int32_t n_iters, uint64_t seed, const uint16_t* sample_idx,
+                                    int32_t pooling, int32_t replace, float read_threshold, float* read_prob,
+                                    float* bag_prob, float* site_prob, int32_t* mod_count, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  if (!model) return M6A_EINVAL;
+  const BagArgs bags = {bag_prob, replace, pooling};
+  return infer_device_impl(model, model->tile_reads, feats, read_off, kmer_idx, n_sites, total_reads, site_id_base, n_samples,
+                           n_iters, seed, sample_idx, read_threshold, read_prob, site_prob, mod_count, workspace,
+                           workspace_bytes, stream, &bags);
+}
+
 extern "C" int32_t m6a_auto_tile_reads(int64_t n_sites, int64_t total_reads, int32_t n_sms) {
   return auto_tile_reads(n_sites, total_reads, n_sms > 0 ? n_sms : 148);
 }
@@ -250,7 +271,16 @@ extern "C" int m6a_sample_indices(uint64_t seed, int64_t site_id, int32_t n_read
                                   int32_t* out, void* stream) {
   if (!out || n_reads < 1 || n_iters < 1 || n_samples < 1) return M6A_EINVAL;
   cudaError_t e = launch_sample_indices(seed, static_cast<uint64_t>(site_id), static_cast<uint32_t>(n_reads), n_iters,
-                                        n_samples, out, static_cast<cudaStream_t>(stream));
+                                        n_samples, false, out, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? M6A_OK : static_cast<int>(e);
+}
+
+extern "C" int m6a_sample_bags(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters, int32_t n_samples,
+                               int32_t* out, void* stream) {
+  if (!out || n_iters < 1 || n_samples < 1 || n_samples > kMaxSamples) return M6A_EINVAL;
+  if (n_reads < n_samples) return M6A_ERANGE;   // no bag of n_samples distinct reads
+  cudaError_t e = launch_sample_indices(seed, static_cast<uint64_t>(site_id), static_cast<uint32_t>(n_reads), n_iters,
+                                        n_samples, true, out, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? M6A_OK : static_cast<int>(e);
 }
 
@@ -282,7 +312,7 @@ static cudaError_t ensure_bytes(void** p, size_t* cap, size_t need) {
   return e;
 }
 
-static cudaError_t slot_reserve(HostSlot& sl, int64_t max_sites, int64_t max_reads) {
+static cudaError_t slot_reserve(HostSlot& sl, int64_t max_sites, int64_t max_reads, int64_t bag_floats_per_site) {
   cudaError_t e = cudaSuccess;
   if (!sl.stream) e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = ensure_bytes(&sl.d_feats, &sl.cap_feats, static_cast<size_t>(max_reads) * kNSig * sizeof(float) + 16);
@@ -292,6 +322,8 @@ static cudaError_t slot_reserve(HostSlot& sl, int64_t max_sites, int64_t max_rea
   if (e == cudaSuccess) e = ensure_bytes(&sl.d_sp, &sl.cap_sp, static_cast<size_t>(max_sites) * sizeof(float));
   if (e == cudaSuccess) e = ensure_bytes(&sl.d_mc, &sl.cap_mc, static_cast<size_t>(max_sites) * sizeof(int32_t));
   if (e == cudaSuccess) e = ensure_bytes(&sl.d_ws, &sl.cap_ws, static_cast<size_t>(m6a_mil_workspace_bytes(max_reads)));
+  if (e == cudaSuccess && bag_floats_per_site > 0)
+    e = ensure_bytes(&sl.d_bag, &sl.cap_bag, static_cast<size_t>(max_sites) * bag_floats_per_site * sizeof(float));
   if (e == cudaSuccess && static_cast<size_t>(max_sites + 1) > sl.cap_hoff) {
     if (sl.h_off) cudaFreeHost(sl.h_off);
     sl.h_off = nullptr;
@@ -308,17 +340,18 @@ void m6a_release_workspace(m6a_model* m) {
     HostSlot& sl = m->slots[s];
     if (sl.stream) cudaStreamSynchronize(sl.stream);
     cudaFree(sl.d_feats); cudaFree(sl.d_off); cudaFree(sl.d_kmer);
-    cudaFree(sl.d_rp); cudaFree(sl.d_sp); cudaFree(sl.d_mc); cudaFree(sl.d_ws);
+    cudaFree(sl.d_rp); cudaFree(sl.d_sp); cudaFree(sl.d_mc); cudaFree(sl.d_ws); cudaFree(sl.d_bag);
     if (sl.h_off) cudaFreeHost(sl.h_off);
     if (sl.stream) cudaStreamDestroy(sl.stream);
     sl = HostSlot();
   }
 }
 
-extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model_c, const float* feats, const int64_t* read_off,
-                                      const int32_t* kmer_idx, int64_t n_sites, int64_t site_id_base,
-                                      int32_t n_samples, int32_t n_iters, uint64_t seed, float read_threshold,
-                                      float* read_prob, float* site_prob, int32_t* mod_count, int32_t n_chunks) {
+// host_bags: nullptr = inference; otherwise the validate()-style bags (bag_prob is then a HOST pointer [n_sites, n_iters] or NULL)
+static int infer_host_impl(const m6a_model_t* model_c, const float* feats, const int64_t* read_off,
+                           const int32_t* kmer_idx, int64_t n_sites, int64_t site_id_base, int32_t n_samples,
+                           int32_t n_iters, uint64_t seed, float read_threshold, float* read_prob, float* site_prob,
+                           int32_t* mod_count, int32_t n_chunks, const BagArgs* host_bags) {
   m6a_model* model = const_cast<m6a_model*>(model_c);
   if (!model || n_sites < 0) return M6A_EINVAL;
   if (n_sites == 0) return M6A_OK;
@@ -328,7 +361,8 @@ extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model_c, const float* f
   if (total_reads < 0) return M6A_EINVAL;
   if (total_reads > 0 && (!feats || !read_prob)) return M6A_EINVAL;
   if (model->dev.emb_dim > 0 && !kmer_idx) return M6A_EINVAL;
-  if (n_samples < 1 || n_samples > 64 || n_iters < 1) return M6A_EINVAL;
+  if (n_samples < 1 || n_samples > kMaxSamples || n_iters < 1) return M6A_EINVAL;
+  float* h_bag = host_bags ? host_bags->bag_prob : nullptr;
 
   // chunk boundaries: balanced by reads, cut at site boundaries (~32 MB of features per chunk by default)
   if (n_chunks <= 0) {
@@ -353,7 +387,8 @@ extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model_c, const float* f
   std::lock_guard<std::mutex> guard(model->ws_mutex);
   const int tile_reads = model->tile_reads;
   const int n_slots = std::min(kHostSlots, n_chunks);
-  for (int s = 0; s < n_slots; ++s) M6A_CUDA(slot_reserve(model->slots[s], max_sites, std::max<int64_t>(1, max_reads)));
+  for (int s = 0; s < n_slots; ++s)
+    M6A_CUDA(slot_reserve(model->slots[s], max_sites, std::max<int64_t>(1, max_reads), h_bag ? n_iters : 0));
 
   int launches = 0;
   int rc = M6A_OK;
@@ -376,13 +411,25 @@ extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model_c, const float* f
       rc = static_cast<int>(e);
       break;
     }
+    BagArgs dev_bags = {nullptr, 1, kPoolProd};
+    if (host_bags) {
+      dev_bags = *host_bags;
+      dev_bags.bag_prob = h_bag ? static_cast<float*>(sl.d_bag) : nullptr;
+    }
     rc = infer_device_impl(model, tile_reads, static_cast<const float*>(sl.d_feats), static_cast<const int64_t*>(sl.d_off),
                            kmer_idx ? static_cast<const int32_t*>(sl.d_kmer) : nullptr, ns, nr, site_id_base + sa,
                            n_samples, n_iters, seed, nullptr, read_threshold, static_cast<float*>(sl.d_rp),
                            static_cast<float*>(sl.d_sp), static_cast<int32_t*>(sl.d_mc), sl.d_ws,
-                           static_cast<int64_t>(sl.cap_ws), sl.stream);
+                           static_cast<int64_t>(sl.cap_ws), sl.stream, host_bags ? &dev_bags : nullptr);
     if (rc != M6A_OK) break;
     ++launches;
+    if (h_bag)
+      e = cudaMemcpyAsync(h_bag + sa * n_iters, sl.d_bag, static_cast<size_t>(ns) * n_iters * sizeof(float),
+                          cudaMemcpyDeviceToHost, sl.stream);
+    if (e != cudaSuccess) {
+      rc = static_cast<int>(e);
+      break;
+    }
     if (nr > 0) e = cudaMemcpyAsync(read_prob + ra, sl.d_rp, nr * sizeof(float), cudaMemcpyDeviceToHost, sl.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(site_prob + sa, sl.d_sp, ns * sizeof(float), cudaMemcpyDeviceToHost, sl.stream);
     if (e == cudaSuccess)
@@ -395,4 +442,23 @@ extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model_c, const float* f
   }
   g_last_launches = launches;
   return rc;
+}
+
+extern "C" int m6a_mil_infer_host_f32(const m6a_model_t* model, const float* feats, const int64_t* read_off,
+                                      const int32_t* kmer_idx, int64_t n_sites, int64_t site_id_base,
+                                      int32_t n_samples, int32_t n_iters, uint64_t seed, float read_threshold,
+                                      float* read_prob, float* site_prob, int32_t* mod_count, int32_t n_chunks) {
+  return infer_host_impl(model, feats, read_off, kmer_idx, n_sites, site_id_base, n_samples, n_iters, seed, read_threshold,
+                         read_prob, site_prob, mod_count, n_chunks, nullptr);
+}
+
+extern "C" int m6a_mil_validate_host_f32(const m6a_model_t* model, const float* feats, const int64_t* read_off,
+                                         const int32_t* kmer_idx, int64_t n_sites, int64_t site_id_base,
+                                         int32_t n_samples, int32_t n_iters, uint64_t seed, int32_t pooling,
+                                         int32_t replace, float read_threshold, float* read_prob, float* bag_prob,
+                                         float* site_prob, int32_t* mod_count, int32_t n_chunks) {
+  if (pooling < kPoolProd || pooling > kPoolMax || (replace != 0 && replace != 1)) return M6A_EINVAL;
+  const BagArgs bags = {bag_prob, replace, pooling};
+  return infer_host_impl(model, feats, read_off, kmer_idx, n_sites, site_id_base, n_samples, n_iters, seed, read_threshold,
+                         read_prob, site_prob, mod_count, n_chunks, &bags);
 }

@@ -205,6 +205,66 @@ __device__ __forceinline__ float mc_lane_generic(const float* qbase, bool from_p
   return v;
 }
 
+// validate()-style bags: `rounds` passes of ONE lane, one bag of k reads per pass, pooled like the model's pooling block
+// (reference model_blocks/pooling_blocks.py:96-98 mean, :127-129 noisy-OR, :158-160 max) on the per-read probabilities
+// this CTA wrote in phase A.  Bag source: explicit indices, Floyd draws without replacement (m6a_rng.cuh), or the
+// inference stream.  Writes each pass to bag_out[32 * pass] (row (site) of bag_prob [n_sites, n_iters], iterations of a
+// lane are 32 apart) and returns the lane's sum over its passes.
+template <int NS>
+__device__ __forceinline__ float bag_rounds(const float* pbase, uint32_t n, Mwc64x& g, int rounds, int k_rt,
+                                            const BagArgs& bags, const uint16_t* __restrict__ explicit_idx,
+                                            size_t explicit_round_stride, float* bag_out) {
+  constexpr int kCap = NS > 0 ? NS : kMaxSamples;
+  const int k = NS > 0 ? NS : k_rt;
+  const bool floyd = explicit_idx == nullptr && bags.replace == 0;
+  const bool paired = n <= kPairedMaxReads;
+  // no bag of k distinct reads exists for n < k (np.random.choice raises in the reference, whose datasets drop such
+  // sites, utils/data_utils.py:129); an empty site has no bag at all
+  const bool no_bag = n == 0u || (floyd && n < static_cast<uint32_t>(k));
+  float v = 0.0f;
+  for (int r = 0; r < rounds; ++r) {
+    uint32_t pick[kCap];
+    float y;
+    if (no_bag) {
+      y = __int_as_float(0x7fc00000);
+    } else {
+      if (explicit_idx != nullptr) {
+#pragma unroll
+        for (int s = 0; s < k; ++s) pick[s] = min(static_cast<uint32_t>(explicit_idx[r * explicit_round_stride + s]), n - 1u);
+      } else if (floyd) {
+        floyd_bag<NS>(g, n, k, pick);
+      } else {
+        uint32_t pending = 0;
+#pragma unroll
+        for (int s = 0; s < k; ++s) {
+          if (!paired) pick[s] = __umulhi(g.next(), n);
+          else if ((s & 1) == 0) g.next_pair(n, pick[s], pending);
+          else pick[s] = pending;
+        }
+      }
+      if (bags.pool == kPoolProd) {
+        float prod = 1.0f;
+#pragma unroll
+        for (int s = 0; s < k; ++s) prod *= 1.0f - pbase[pick[s]];
+        y = 1.0f - prod;
+      } else if (bags.pool == kPoolMean) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int s = 0; s < k; ++s) sum += pbase[pick[s]];
+        y = sum / static_cast<float>(k);
+      } else {
+        float m = pbase[pick[0]];
+#pragma unroll
+        for (int s = 1; s < k; ++s) m = fmaxf(m, pbase[pick[s]]);
+        y = m;
+      }
+    }
+    if (bag_out != nullptr) bag_out[32 * r] = y;
+    v += y;
+  }
+  return v;
+}
+
 // ---- feature staging geometry: rows [r0 + chunk*kChunkReads, ...) of feats as 16-byte granules -----------
 struct Span {
   unsigned long long b0, b1;   // exact byte range of the rows
@@ -293,12 +353,14 @@ __device__ __forceinline__ void encode_reads(Smem& sm, const WeightImage& W, con
 }
 
 // -------------------------------------------------------------------------------------------------
-template <int NS>
+// BAGS = false: inference (phase B = Monte-Carlo noisy-OR, draws with replacement).  BAGS = true: the validate()-style
+// literal MIL forward (phase B = bag_rounds); `bags` is read by that instantiation only.
+template <int NS, bool BAGS>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 #if M6A_WEIGHTS_CONST
-mil_infer_kernel(const KernelArgs a, const __grid_constant__ WeightImage wparam) {
+mil_infer_kernel(const KernelArgs a, const __grid_constant__ WeightImage wparam, const BagArgs bags) {
 #else
-mil_infer_kernel(const KernelArgs a) {
+mil_infer_kernel(const KernelArgs a, const BagArgs bags) {
 #endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -357,7 +419,7 @@ mil_infer_kernel(const KernelArgs a) {
     }
     __syncthreads();
     const int nr = sm.roff[ns];                 // reads in this tile
-    const bool q_in_smem = nr <= kQCap;
+    const bool q_in_smem = !BAGS && nr <= kQCap;   // bags pool the per-read p itself (read back from read_prob)
     const int n_chunks = (nr + kChunkReads - 1) / kChunkReads;
 
     // ---- feature staging: rows [ra, ra+rows) of feats -> sm.feat[head + i*9 + k] ---------------------
@@ -460,8 +522,32 @@ mil_infer_kernel(const KernelArgs a) {
     }
     __syncthreads();  // q, cnt and (fallback) read_prob of the whole tile are visible
 
+    // ---- phase B (bags): one bag per (site, pass), pooled; warp per (site, block of passes) --------------
+    if constexpr (BAGS) {
+      const int items = ns * n_blocks;
+      for (int item = warp; item < items; item += kWarps) {
+        const int sl_ = item / n_blocks, blk_ = item - sl_ * n_blocks;
+        const int n = sm.roff[sl_ + 1] - sm.roff[sl_];
+        float v;
+        {
+          // passes of this lane in block blk_: it = (blk_*ipl + r)*32 + lane, r < ipl, it < n_iters
+          const long long it0 = static_cast<long long>(blk_) * ipl * 32 + lane;
+          const long long left = (static_cast<long long>(a.n_iters) - it0 + 31) / 32;
+          const int rounds = static_cast<int>(left < 0 ? 0 : (left > ipl ? ipl : left));
+          Mwc64x g;
+          g.seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk_),
+                 static_cast<unsigned long long>(a.site_id_base + s0 + sl_), a.seed);
+          const size_t row = static_cast<size_t>(s0 + sl_) * a.n_iters + it0;
+          const uint16_t* ex = a.sample_idx != nullptr ? a.sample_idx + row * a.n_samples : nullptr;
+          float* bag_out = bags.bag_prob != nullptr ? bags.bag_prob + row : nullptr;
+          v = bag_rounds<NS>(a.read_prob + r0 + sm.roff[sl_], static_cast<uint32_t>(n), g, rounds, a.n_samples, bags, ex,
+                             static_cast<size_t>(32) * a.n_samples, bag_out);
+        }
+        v = warp_butterfly_sum(v);
+        if (lane == 0) sm.partial[sl_][blk_] = v;
+      }
+    } else {
     // ---- phase B: Monte-Carlo noisy-OR ----------------------------------------------------------
-    {
       // items (site, block) are dealt round-robin to the warps, two at a time; (sl, blk) advance without a division
       const int items = ns * n_blocks;
       auto advance = [&](int& sl_, int& blk_) {
@@ -570,7 +656,7 @@ __global__ void tile_bounds_kernel(const int64_t* __restrict__ read_off, long lo
 }
 
 __global__ void sample_indices_kernel(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
-                                      int n_blocks, int ipl, int32_t* __restrict__ out) {
+                                      int n_blocks, int ipl, bool without_replacement, int32_t* __restrict__ out) {
   // one thread per (block, lane) stream, exactly the order phase B consumes it
   const int stream = blockIdx.x * blockDim.x + threadIdx.x;
   if (stream >= n_blocks * 32) return;
@@ -580,6 +666,12 @@ __global__ void sample_indices_kernel(uint64_t seed, uint64_t site_id, uint32_t 
   for (int k = 0; k < ipl; ++k) {
     const long long it = (static_cast<long long>(blk) * ipl + k) * 32 + lane;
     if (it >= n_iters) break;
+    if (without_replacement) {   // Floyd bag, exactly as bag_rounds draws it
+      uint32_t pick[kMaxSamples];
+      floyd_bag<0>(g, n_reads, n_samples, pick);
+      for (int s = 0; s < n_samples; ++s) out[it * n_samples + s] = static_cast<int32_t>(pick[s]);
+      continue;
+    }
     uint32_t pending = 0;
     for (int s = 0; s < n_samples; ++s) {
       uint32_t i;
@@ -594,30 +686,25 @@ __global__ void sample_indices_kernel(uint64_t seed, uint64_t site_id, uint32_t 
 // ---- host-side launchers ---------------------------------------------------------------------------
 // occupancy / max-dynamic-smem attribute are per (device, kernel instantiation)
 constexpr int kMaxDevices = 64;
-static int g_max_ctas_per_sm[kMaxDevices][2];
-static bool g_attr_done[kMaxDevices][2];
+constexpr int kVariants = 4;   // {n_samples == 20, generic} x {inference, bags}
+static int g_max_ctas_per_sm[kMaxDevices][kVariants];
+static bool g_attr_done[kMaxDevices][kVariants];
 
-cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image, int n_sms, cudaStream_t stream,
-                             LaunchInfo* info) {
-  const bool fast = (a.n_samples == 20);
-  auto kfast = mil_infer_kernel<20>;
-  auto kgen = mil_infer_kernel<0>;
-  const void* fn = fast ? reinterpret_cast<const void*>(kfast) : reinterpret_cast<const void*>(kgen);
+template <int NS, bool BAGS>
+static cudaError_t launch_variant(const KernelArgs& a, const WeightImage* host_image, const BagArgs& bags, int n_sms,
+                                  int dev, cudaStream_t stream, LaunchInfo* info) {
+  auto kern = mil_infer_kernel<NS, BAGS>;
+  constexpr int variant = (NS == 20 ? 0 : 1) + (BAGS ? 2 : 0);
   const int smem = static_cast<int>(sizeof(Smem));
-  int dev = 0;
-  cudaError_t de = cudaGetDevice(&dev);
-  if (de != cudaSuccess) return de;
-  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
-  int& occ = g_max_ctas_per_sm[dev][fast ? 0 : 1];
-  if (!g_attr_done[dev][fast ? 0 : 1]) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int& occ = g_max_ctas_per_sm[dev][variant];
+  if (!g_attr_done[dev][variant]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     int nb = 0;
-    e = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfast, kThreads, smem)
-             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kgen, kThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
     if (e != cudaSuccess) return e;
     occ = nb > 0 ? nb : 1;
-    g_attr_done[dev][fast ? 0 : 1] = true;
+    g_attr_done[dev][variant] = true;
   }
   long long grid = static_cast<long long>(n_sms) * occ;
   if (grid > a.n_tiles) grid = a.n_tiles;
@@ -629,18 +716,28 @@ cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image,
     info->tile_reads = a.tile_reads;
   }
 #if M6A_WEIGHTS_CONST
-  if (fast)
-    kfast<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a, *host_image);
-  else
-    kgen<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a, *host_image);
+  kern<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a, *host_image, bags);
 #else
   (void)host_image;
-  if (fast)
-    kfast<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a);
-  else
-    kgen<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a);
+  kern<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(a, bags);
 #endif
   return cudaGetLastError();
+}
+
+cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image, const BagArgs* bags, int n_sms,
+                             cudaStream_t stream, LaunchInfo* info) {
+  int dev = 0;
+  cudaError_t de = cudaGetDevice(&dev);
+  if (de != cudaSuccess) return de;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  const bool fast = (a.n_samples == 20);
+  if (bags != nullptr) {
+    return fast ? launch_variant<20, true>(a, host_image, *bags, n_sms, dev, stream, info)
+                : launch_variant<0, true>(a, host_image, *bags, n_sms, dev, stream, info);
+  }
+  const BagArgs none = {nullptr, 1, kPoolProd};
+  return fast ? launch_variant<20, false>(a, host_image, none, n_sms, dev, stream, info)
+              : launch_variant<0, false>(a, host_image, none, n_sms, dev, stream, info);
 }
 
 cudaError_t launch_tile_bounds(const int64_t* read_off, long long n_sites, long long n_tiles, int tile_reads,
@@ -652,12 +749,12 @@ cudaError_t launch_tile_bounds(const int64_t* read_off, long long n_sites, long 
 }
 
 cudaError_t launch_sample_indices(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
-                                  int32_t* out, cudaStream_t stream) {
+                                  bool without_replacement, int32_t* out, cudaStream_t stream) {
   int ipl, n_blocks;
   block_layout(n_iters, &ipl, &n_blocks);
   const int streams = n_blocks * 32;
   sample_indices_kernel<<<(streams + 127) / 128, 128, 0, stream>>>(seed, site_id, n_reads, n_iters, n_samples,
-                                                                  n_blocks, ipl, out);
+                                                                  n_blocks, ipl, without_replacement, out);
   return cudaGetLastError();
 }
 

@@ -75,16 +75,28 @@ struct KernelArgs {
   bool feats_tma_ok;   // feats base 16-byte aligned -> cp.async.bulk staging
 };
 
+// validate()-style bags (m6a_mil_validate_f32): the literal MIL forward of the reference's evaluation loop
+// (utils/training_utils.py:236-256) -- per pass one bag of n_samples reads per site, pooled by the model's pooling block.
+// Passed as a third kernel parameter so that the inference instantiations keep their parameter layout.
+enum PoolKind : int { kPoolProd = 0, kPoolMean = 1, kPoolMax = 2 };
+struct BagArgs {
+  float* bag_prob;   // [n_sites, n_iters] per-pass pooled probability (nullptr: only the mean over passes is kept)
+  int replace;       // 0: bags without replacement (Floyd draws, m6a_rng.cuh); 1: the inference index stream
+  int pool;          // PoolKind
+};
+
 struct LaunchInfo {
   int grid, block, smem_bytes, tile_reads;
 };
 
 size_t smem_bytes();
-cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image, int n_sms, cudaStream_t stream,
-                             LaunchInfo* info);
+// bags == nullptr: inference (Monte-Carlo noisy-OR with replacement); otherwise the validate()-style bags instantiation
+cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image, const BagArgs* bags, int n_sms,
+                             cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_tile_bounds(const int64_t* read_off, long long n_sites, long long n_tiles, int tile_reads,
                                long long* tile_bounds, cudaStream_t stream);
+// without_replacement: the Floyd bag stream instead of the inference stream
 cudaError_t launch_sample_indices(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples,
-                                  int32_t* out, cudaStream_t stream);
+                                  bool without_replacement, int32_t* out, cudaStream_t stream);
 
 }  // namespace m6a

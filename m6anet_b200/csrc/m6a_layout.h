@@ -7,6 +7,7 @@ namespace m6a {
 constexpr int kNSig = 9;          // signal features per read (reference model_blocks/blocks.py:111: 3 * (2*1+1))
 constexpr int kH2 = 32;           // second Linear width (reference m6anet.toml: output_channel = 32)
 constexpr int kH1Max = 152;       // first Linear width limit (shipped: 150)
+constexpr int kMaxSamples = 64;   // reads per bag limit (the reference uses 20: utils/inference_utils.py:54, min_reads)
 constexpr int kKmerPos = 3;       // five-mers per site (centre + 1 flank each side)
 constexpr int kPairs = kH1Max / 2; // hidden units are processed two at a time (packed FFMA2)
 constexpr int kPairFloats = 84;    // per pair p=(j0,j1): 9 x (w1[j0,k], w1[j1,k]), 2 pad, w2[0..31,j0], w2[0..31,j1]

@@ -16,6 +16,14 @@
 #pragma once
 #include <stdint.h>
 
+// The generator compiles for the host too (tests/native/bags_emul.cpp builds the same source with g++ and compares it
+// with oracle/philox.py on the CPU); device code is unchanged by the host branches.
+#if defined(__CUDACC__)
+#define M6A_HD __host__ __device__ __forceinline__
+#else
+#define M6A_HD inline
+#endif
+
 namespace m6a {
 
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
@@ -31,7 +39,7 @@ struct Philox4 {
   uint32_t x, y, z, w;
 };
 
-__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+M6A_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                          uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -49,17 +57,26 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
   return Philox4{c0, c1, c2, c3};
 }
 
+M6A_HD uint32_t mulhi_u32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32);
+#endif
+}
+
 struct Mwc64x {
   uint32_t x, c;
-  __device__ __forceinline__ void seed(uint32_t lane, uint32_t block, uint64_t site, uint64_t key) {
+  M6A_HD void seed(uint32_t lane, uint32_t block, uint64_t site, uint64_t key) {
     const Philox4 w = philox4x32_10(lane, block, static_cast<uint32_t>(site), static_cast<uint32_t>(site >> 32),
                                     static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
     x = w.x;
-    c = __umulhi(w.y, kMwcA - 1u);
+    c = mulhi_u32(w.y, kMwcA - 1u);
     if ((x | c) == 0u) x = 1u;
   }
-  __device__ __forceinline__ uint32_t next() {
+  M6A_HD uint32_t next() {
     const uint32_t word = x ^ c;
+#if defined(__CUDA_ARCH__)
     // (c:x) = A * x + c as one wide multiply (FMA pipe) plus an add-with-carry pair (ALU pipe).  The
     // fused form IMAD.WIDE Rd, x, A, (c,0) needs the addend in an aligned register pair, which costs
     // two extra moves per draw on the FMA pipe.
@@ -69,15 +86,39 @@ struct Mwc64x {
     asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(nx), "=r"(nc) : "r"(lo), "r"(c), "r"(hi));
     x = nx;
     c = nc;
+#else
+    const uint64_t t = static_cast<uint64_t>(kMwcA) * x + c;
+    x = static_cast<uint32_t>(t);
+    c = static_cast<uint32_t>(t >> 32);
+#endif
     return word;
   }
   // two indices from one word (paired regime): the wide product's high half is the first index, its low half is a
   // fresh uniform word for the second
-  __device__ __forceinline__ void next_pair(uint32_t n, uint32_t& i1, uint32_t& i2) {
+  M6A_HD void next_pair(uint32_t n, uint32_t& i1, uint32_t& i2) {
     const uint64_t t = static_cast<uint64_t>(next()) * n;
     i1 = static_cast<uint32_t>(t >> 32);
-    i2 = __umulhi(static_cast<uint32_t>(t), n);
+    i2 = mulhi_u32(static_cast<uint32_t>(t), n);
   }
 };
+
+// ---- bags without replacement (validate()-style literal MIL forward; specification: oracle/philox.py "Floyd bags") ----
+// R. Floyd's algorithm: k distinct picks out of n, every k-subset equally likely, one 32-bit word per pick:
+//   for d in 0..k-1:  j = n-k+d;  t = (word * (j+1)) >> 32;  pick_d = (t already picked) ? j : t
+// Replaces np.random.choice(len(features), min_reads, replace=False) of the reference's evaluation datasets
+// (utils/data_utils.py:213-214).  NS > 0: compile-time bag size (picks stay in registers); NS == 0: run-time k <= 64.
+template <int NS, class Gen>
+M6A_HD void floyd_bag(Gen& g, uint32_t n, int k_rt, uint32_t* pick) {
+  const int k = NS > 0 ? NS : k_rt;
+#pragma unroll
+  for (int d = 0; d < k; ++d) {
+    const uint32_t j = n - static_cast<uint32_t>(k) + static_cast<uint32_t>(d);
+    const uint32_t t = mulhi_u32(g.next(), j + 1u);
+    bool dup = false;
+#pragma unroll
+    for (int e = 0; e < d; ++e) dup |= (pick[e] == t);
+    pick[d] = dup ? j : t;
+  }
+}
 
 }  // namespace m6a

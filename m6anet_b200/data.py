@@ -16,7 +16,9 @@ Besides the reference's per-site `__getitem__` (Python json, reference-shaped), 
 kmer_idx [S,3] i32).  `load_sites` runs the multi-threaded native parser `m6a_ingest_parts`
 (m6anet_b200/csrc/m6a_io.cpp); tests/test_host.py checks it bit for bit against the per-site Python path and
 against the reference's own NanopolishDS output.
-Training modes and on-the-fly norm-factor computation are outside the inference path and not provided.
+The evaluation modes of the reference ('Train' / 'Val' / 'Test': data.info.labelled filtered by set_type, labels from
+modification_status, data_utils.py:124-126,102-103) are provided for `m6anet_b200.validation.validate`; training itself
+and on-the-fly norm-factor computation are outside the path and not provided.
 """
 from __future__ import annotations
 
@@ -59,13 +61,13 @@ def load_norm_factors(norm_path: str) -> Dict[str, Tuple[np.ndarray, np.ndarray]
     return {str(k): (np.asarray(v[0], dtype=np.float64), np.asarray(v[1], dtype=np.float64)) for k, v in nd.items()}
 
 
-def read_info(root_dir: str):
+def read_info(root_dir: str, name: str = "data.info"):
     """data.info -> (transcript_id bytes array 'S<w>', transcript_position, start, end, n_reads) int64 arrays.
     Native reader (m6a_info_count / m6a_info_read); the reference uses pd.read_csv (utils/data_utils.py:118-129)."""
     import ctypes as C
     from . import _cabi
     L = _cabi.lib()
-    path = os.fsencode(os.path.join(root_dir, "data.info"))
+    path = os.fsencode(os.path.join(root_dir, name))
     n, nb = C.c_int64(0), C.c_int64(0)
     _cabi.check(L.m6a_info_count(path, C.byref(n), C.byref(nb)), f"m6a_info_count({os.fsdecode(path)})")
     n, nb = int(n.value), int(nb.value)
@@ -85,14 +87,33 @@ def read_info(root_dir: str):
     return tx, cols[0][:n], cols[1][:n], cols[2][:n], cols[3][:n]
 
 
+def read_labels(root_dir: str, name: str = "data.info.labelled"):
+    """(modification_status int64 [n], set_type str [n]) of data.info.labelled, rows aligned with read_info(root_dir, name)
+    (blank lines skipped like the native reader does).  Reference: pd.read_csv at utils/data_utils.py:125."""
+    import csv
+    status, set_type = [], []
+    with open(os.path.join(root_dir, name), newline="") as f:
+        rows = csv.reader(f)
+        header = [h.strip() for h in next(rows)]
+        try:
+            i_status, i_set = header.index("modification_status"), header.index("set_type")
+        except ValueError:
+            raise ValueError(f"{os.path.join(root_dir, name)} needs the columns modification_status and set_type")
+        for row in rows:
+            if not row or (len(row) == 1 and not row[0].strip()):
+                continue
+            status.append(int(float(row[i_status])))
+            set_type.append(row[i_set].strip())
+    return np.array(status, dtype=np.int64), np.array(set_type, dtype=str)
+
+
 class NanopolishDS:
-    allowed_mode = ('Inference',)
+    allowed_mode = ('Train', 'Test', 'Val', 'Inference')     # reference data_utils.py:42
 
     def __init__(self, root_dir, min_reads: int = 20, norm_path: Optional[str] = None, num_neighboring_features: int = 1,
                  mode: str = 'Inference', n_processes: int = 1):
         if mode not in self.allowed_mode:
-            raise ValueError(f"Invalid mode passed to dataset, must be one of {self.allowed_mode} "
-                             f"(training modes are outside the m6anet_b200 inference path)")
+            raise ValueError(f"Invalid mode passed to dataset, must be one of {self.allowed_mode}")
         if root_dir is None:
             raise ValueError("Either root directory or data info must be given")
         if norm_path is None:
@@ -113,9 +134,18 @@ class NanopolishDS:
 
     # ---- index ------------------------------------------------------------------------------------
     def initialize_data_info(self):
-        tx, pos, start, end, n_reads = read_info(self.root_dir)
+        if self.mode == 'Inference':
+            tx, pos, start, end, n_reads = read_info(self.root_dir)
+            keep = n_reads >= self.min_reads                                               # data_utils.py:129
+            self.labels = None
+        else:    # labelled index filtered by set_type (data_utils.py:124-126); labels = modification_status (:102-103)
+            tx, pos, start, end, n_reads = read_info(self.root_dir, "data.info.labelled")
+            status, set_type = read_labels(self.root_dir)
+            if len(status) != len(pos):
+                raise ValueError("data.info.labelled: label columns and index columns disagree on the number of rows")
+            keep = (set_type == self.mode) & (n_reads >= self.min_reads)
+            self.labels = status[keep]
         self.data_fpath = os.path.join(self.root_dir, "data.json")
-        keep = n_reads >= self.min_reads                                                   # data_utils.py:129
         self._tx_bytes = tx[keep]
         self._pos = pos[keep]
         self._n_reads = n_reads[keep]
@@ -139,7 +169,11 @@ class NanopolishDS:
     def data_info(self):
         """pandas view of the site index (reference attribute name); built on demand"""
         import pandas as pd
-        return pd.DataFrame({"transcript_id": self._tx, "transcript_position": self._pos, "n_reads": self._n_reads})
+        df = pd.DataFrame({"transcript_id": self._tx, "transcript_position": self._pos, "n_reads": self._n_reads})
+        if self.labels is not None:
+            df["modification_status"] = self.labels
+            df["set_type"] = self.mode
+        return df
 
     def __len__(self) -> int:
         return len(self._pos)
@@ -226,9 +260,14 @@ class NanopolishDS:
         return tx_id, tx_pos, read_ids, feats, kid
 
     def __getitem__(self, idx: int):
-        """Reference-shaped item (data_utils.py:192-231): features [n,9] f32, kmer [n,3] i64 (row repeated),
-        tx_id [n], tx_pos [n], read_ids [n]."""
+        """Reference-shaped item (data_utils.py:192-231).  Inference: features [n,9] f32, kmer [n,3] i64 (row repeated),
+        tx_id [n], tx_pos [n], read_ids [n].  Labelled modes: a bag of min_reads reads drawn without replacement from
+        the process-global NumPy stream (:213-214), its k-mer rows and the site's label -- the reference-shaped view
+        only; `validation.validate` draws its bags on the device instead."""
         tx_id, tx_pos, read_ids, feats, kid = self._site(idx)
+        if self.mode != 'Inference':
+            feats = feats[np.random.choice(len(feats), self.min_reads, replace=False), :]
+            return feats, np.repeat(kid[None, :], len(feats), axis=0), int(self.labels[idx])
         n = len(feats)
         return feats, np.repeat(kid[None, :], n, axis=0), np.repeat(tx_id, n), np.repeat(tx_pos, n), read_ids
 
@@ -320,12 +359,21 @@ class NanopolishReplicateDS(NanopolishDS):
 
     def initialize_data_info(self):
         # outer join of the directories on (transcript_id, transcript_position), sites in first-appearance order
-        cols = [read_info(d) for d in self.root_dir]
+        labelled = self.mode != 'Inference'
+        cols = [read_info(d, "data.info.labelled" if labelled else "data.info") for d in self.root_dir]
         width = max(c[0].dtype.itemsize for c in cols)
         tx = np.concatenate([c[0].astype(f"S{width}") for c in cols])
         pos, start, end, n_reads = (np.concatenate([c[k] for c in cols]) for k in (1, 2, 3, 4))
         rep = np.concatenate([np.full(len(c[1]), r, dtype=np.int32) for r, c in enumerate(cols)])
-        key = np.rec.fromarrays([tx, pos], names="tx,pos")
+        if labelled:   # the join key also carries modification_status and set_type (data_utils.py:349-350)
+            lab = [read_labels(d) for d in self.root_dir]
+            status = np.concatenate([l[0] for l in lab])
+            set_type = np.concatenate([l[1] for l in lab])
+            if len(status) != len(pos):
+                raise ValueError("data.info.labelled: label columns and index columns disagree on the number of rows")
+            key = np.rec.fromarrays([tx, pos, status, set_type], names="tx,pos,status,set_type")
+        else:
+            key = np.rec.fromarrays([tx, pos], names="tx,pos")
         uniq, first, inverse = np.unique(key, return_index=True, return_inverse=True)
         order = np.argsort(first, kind="stable")                 # unique keys by first appearance
         rank = np.empty(len(uniq), dtype=np.int64)
@@ -333,6 +381,11 @@ class NanopolishReplicateDS(NanopolishDS):
         site = rank[inverse.reshape(-1)]
         total = np.bincount(site, weights=n_reads, minlength=len(uniq)).astype(np.int64)
         keep = total >= self.min_reads                                                   # data_utils.py:373
+        if labelled:
+            keep &= (uniq["set_type"][order] == self.mode)                                  # data_utils.py:370-371
+            self.labels = uniq["status"][order][keep].astype(np.int64)
+        else:
+            self.labels = None
         new_id = np.cumsum(keep) - 1
         self._tx_bytes = uniq["tx"][order][keep]
         self._pos = uniq["pos"][order][keep].astype(np.int64)

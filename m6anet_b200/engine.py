@@ -11,6 +11,15 @@ from . import _cabi
 from .weights import EncoderWeights
 
 DEFAULT_N_SAMPLES = 20   # the literal 20 of reference utils/inference_utils.py:54
+POOLING = {"prod": 0, "mean": 1, "max": 2}   # M6A_POOL_* (reference SigmoidProdPooling / SigmoidMeanPooling / SigmoidMaxPooling)
+
+
+def _pool_code(pooling) -> int:
+    if isinstance(pooling, str):
+        if pooling not in POOLING:
+            raise ValueError(f"unknown pooling {pooling!r}; one of {sorted(POOLING)}")
+        return POOLING[pooling]
+    return int(pooling)
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -139,6 +148,84 @@ class MilEngine:
             seed & 0xFFFFFFFFFFFFFFFF, read_threshold, _ptr(read_prob), _ptr(site_prob), _ptr(mod_count), n_chunks)
         _cabi.check(rc, "m6a_mil_infer_host_f32")
         return read_prob, site_prob, mod_count
+
+    # ---- validate()-style literal MIL forward (m6a_mil_validate_f32 / m6a_mil_validate_host_f32) ----------------
+    def validate_device(self, feats, read_off, kmer_idx, n_iters: int, seed: int = 0, site_id_base: int = 0,
+                        n_samples: int = DEFAULT_N_SAMPLES, pooling="prod", replace: bool = False,
+                        read_threshold: float = 0.033379376, sample_idx=None, stream=None):
+        """CUDA tensors as infer_device.  Every pass pools one bag of n_samples reads per site (drawn without
+        replacement unless replace=True or explicit `sample_idx` [sites, n_iters, n_samples] uint16 bags are given).
+        Returns (read_prob [R], bag_prob [sites, n_iters], site_mean [sites], mod_count [sites]) without synchronising."""
+        torch = self._torch
+
+        def need(cond, msg):
+            if not cond:
+                raise ValueError("MilEngine.validate_device: " + msg)
+
+        need(feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous() and feats.dim() == 2 and feats.shape[1] == 9,
+             "feats must be a contiguous float32 CUDA tensor [reads, 9]")
+        need(read_off.is_cuda and read_off.dtype == torch.int64 and read_off.is_contiguous() and read_off.numel() >= 1,
+             "read_off must be a contiguous int64 CUDA tensor [sites + 1]")
+        need(feats.device == self.device and read_off.device == self.device, f"tensors must live on {self.device}")
+        n_sites = read_off.numel() - 1
+        total_reads = feats.shape[0]
+        if kmer_idx is not None:
+            need(kmer_idx.is_cuda and kmer_idx.dtype == torch.int32 and kmer_idx.is_contiguous() and kmer_idx.numel() == 3 * n_sites,
+                 "kmer_idx must be a contiguous int32 CUDA tensor [sites, 3]")
+        if sample_idx is not None:
+            need(sample_idx.is_cuda and sample_idx.dtype == torch.uint16 and sample_idx.is_contiguous()
+                 and sample_idx.numel() == n_sites * n_iters * n_samples,
+                 "sample_idx must be a contiguous uint16 CUDA tensor [sites, n_iters, n_samples]")
+        read_prob = torch.empty(total_reads, dtype=torch.float32, device=self.device)
+        bag_prob = torch.empty((n_sites, n_iters), dtype=torch.float32, device=self.device)
+        site_prob = torch.empty(n_sites, dtype=torch.float32, device=self.device)
+        mod_count = torch.empty(n_sites, dtype=torch.int32, device=self.device)
+        ws_bytes = int(self._lib.m6a_mil_workspace_bytes(total_reads))
+        workspace = torch.empty(ws_bytes // 8, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device) if stream is None else stream
+            if stream is not None:
+                for t in (workspace, read_prob, bag_prob, site_prob, mod_count):
+                    t.record_stream(st)
+            rc = self._lib.m6a_mil_validate_f32(
+                self._handle, feats.data_ptr(), read_off.data_ptr(), None if kmer_idx is None else kmer_idx.data_ptr(),
+                n_sites, total_reads, site_id_base, n_samples, n_iters, seed & 0xFFFFFFFFFFFFFFFF,
+                None if sample_idx is None else sample_idx.data_ptr(), _pool_code(pooling), 1 if replace else 0,
+                read_threshold, read_prob.data_ptr(), bag_prob.data_ptr(), site_prob.data_ptr(), mod_count.data_ptr(),
+                workspace.data_ptr(), ws_bytes, st.cuda_stream)
+        _cabi.check(rc, "m6a_mil_validate_f32")
+        return read_prob, bag_prob, site_prob, mod_count
+
+    def validate_host(self, feats: np.ndarray, read_off: np.ndarray, kmer_idx: Optional[np.ndarray], n_iters: int,
+                      seed: int = 0, site_id_base: int = 0, n_samples: int = DEFAULT_N_SAMPLES, pooling="prod",
+                      replace: bool = False, read_threshold: float = 0.033379376, n_chunks: int = 0):
+        """NumPy buffers; returns (read_prob [R], bag_prob [sites, n_iters], site_mean [sites], mod_count [sites])."""
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        n_sites = len(read_off) - 1
+        if kmer_idx is not None:
+            kmer_idx = np.ascontiguousarray(kmer_idx, dtype=np.int32)
+        read_prob = np.empty(feats.shape[0], dtype=np.float32)
+        bag_prob = np.empty((n_sites, n_iters), dtype=np.float32)
+        site_prob = np.empty(n_sites, dtype=np.float32)
+        mod_count = np.empty(n_sites, dtype=np.int32)
+        self._select()
+        rc = self._lib.m6a_mil_validate_host_f32(
+            self._handle, _ptr(feats), _ptr(read_off), _ptr(kmer_idx), n_sites, site_id_base, n_samples, n_iters,
+            seed & 0xFFFFFFFFFFFFFFFF, _pool_code(pooling), 1 if replace else 0, read_threshold, _ptr(read_prob),
+            _ptr(bag_prob), _ptr(site_prob), _ptr(mod_count), n_chunks)
+        _cabi.check(rc, "m6a_mil_validate_host_f32")
+        return read_prob, bag_prob, site_prob, mod_count
+
+    def sample_bags(self, seed: int, site_id: int, n_reads: int, n_iters: int, n_samples: int = DEFAULT_N_SAMPLES):
+        """The device without-replacement bags of one site, int32 CUDA tensor [n_iters, n_samples]."""
+        torch = self._torch
+        out = torch.empty((n_iters, n_samples), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.m6a_sample_bags(seed & 0xFFFFFFFFFFFFFFFF, site_id, n_reads, n_iters, n_samples,
+                                           out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        _cabi.check(rc, "m6a_sample_bags")
+        return out
 
     def sample_indices(self, seed: int, site_id: int, n_reads: int, n_iters: int, n_samples: int = DEFAULT_N_SAMPLES):
         torch = self._torch

@@ -17,7 +17,7 @@ Parity status: PINNED.  ``tests/test_oracle.py`` checks the restatement against
  (c) Random123 known-answer vectors for Philox4x32-10 and D. B. Thomas' MWC64X recurrence.
 """
 from .philox import (philox4x32_10, sample_indices, sample_indices_many, sample_indices_mt19937,  # noqa: F401
-                     block_layout)
+                     block_layout, bag_indices, bag_indices_many, bag_indices_mt19937)
 from .mil_oracle import (  # noqa: F401
     ReadEncoderParams,
     read_probabilities,
@@ -25,4 +25,6 @@ from .mil_oracle import (  # noqa: F401
     mod_ratio,
     mil_inference,
     closed_form_site_probability,
+    pool_bags,
+    mil_validate,
 )

@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .philox import sample_indices_many
+from .philox import bag_indices_many, sample_indices_many
 
 
 @dataclass
@@ -143,3 +143,68 @@ def mil_inference(params: ReadEncoderParams, feats: np.ndarray, read_off: np.nda
             idx = sample_idx[s] if sample_idx is not None else idx_b[s - s0]
             site_prob[s] = noisy_or_site_probability(p, idx)
     return read_prob, site_prob, mod_count
+
+
+def pool_bags(read_prob: np.ndarray, idx: np.ndarray, pool: str = "prod") -> np.ndarray:
+    """Site-level output of the pooling filter on gathered bags, float32 [n_bags].
+
+    ``idx`` [n_bags, n_reads_per_site] selects the reads of each bag; the three instance-based pooling blocks are
+        prod  1 - prod(1 - p, axis=1)   SigmoidProdPooling.forward  model_blocks/pooling_blocks.py:127-129
+        mean  mean(p, axis=1)           SigmoidMeanPooling.forward  model_blocks/pooling_blocks.py:96-98
+        max   max(p, axis=1)            SigmoidMaxPooling.forward   model_blocks/pooling_blocks.py:158-160
+    (``MILModel.forward`` -> ``get_site_probability`` = pooling_filter(read_representation) with an empty decoder,
+    model/model.py:140-164).  All float32 like the torch ops.
+    """
+    p = np.asarray(read_prob, dtype=np.float32)[np.asarray(idx)]
+    if pool == "prod":
+        return (np.float32(1) - np.prod(np.float32(1) - p, axis=1)).astype(np.float32)
+    if pool == "mean":
+        return np.mean(p, axis=1, dtype=np.float32)
+    if pool == "max":
+        return np.max(p, axis=1)
+    raise ValueError(f"unknown pooling {pool!r}")
+
+
+def mil_validate(params: ReadEncoderParams, feats: np.ndarray, read_off: np.ndarray, kmer_idx: Optional[np.ndarray],
+                 n_iters: int, seed: int = 0, site_id_base: int = 0, n_samples: int = 20, pool: str = "prod",
+                 read_threshold: float = 0.033379376, sample_idx: Optional[Sequence[np.ndarray]] = None):
+    """validate()-style literal MIL forward on flat buffers, the oracle twin of ``m6a_mil_validate_f32``.
+
+    Restates the evaluation loop of the reference (utils/training_utils.py:236-256): every pass draws, per site, a bag
+    of ``min_reads`` reads WITHOUT replacement (utils/data_utils.py:213-214), runs ``MILModel.forward`` on it
+    (model/model.py:155-164: read encoder -> pooling filter) and the passes are averaged
+    (``np.mean(all_y_pred, axis=0)``, float32 rows added in pass order).  The read encoder is evaluated once per read
+    (eval mode: BatchNorm running statistics, no dropout => a read's probability does not depend on its bag).
+    Bags: ``sample_idx[s]`` [n_iters, n_samples] if given, else the device Floyd stream of site ``site_id_base + s``
+    (oracle/philox.py: bag_indices).
+
+    Returns (read_prob f32 [R], bag_prob f32 [n_sites, n_iters], site_mean f32 [n_sites], mod_count i32 [n_sites]).
+    """
+    read_off = np.asarray(read_off, dtype=np.int64)
+    n_sites = len(read_off) - 1
+    n_reads = np.diff(read_off)
+    kmer_rows = None
+    if params.emb is not None:
+        kmer_rows = np.repeat(np.asarray(kmer_idx).reshape(n_sites, 3), n_reads, axis=0)
+    read_prob = read_probabilities(params, feats, kmer_rows)
+    bag_prob = np.full((n_sites, n_iters), np.nan, dtype=np.float32)
+    mod_count = np.zeros(n_sites, dtype=np.int32)
+    thr = np.float32(read_threshold)
+    ok = n_reads >= n_samples
+    idx_all = None
+    if sample_idx is None and ok.any():
+        sel = np.nonzero(ok)[0]
+        idx_all = dict(zip(sel.tolist(), bag_indices_many(seed, site_id_base + sel, n_reads[sel], n_iters, n_samples)))
+    for s in range(n_sites):
+        p = read_prob[read_off[s]:read_off[s + 1]]
+        mod_count[s] = int(np.count_nonzero(p >= thr))
+        if sample_idx is not None:
+            if len(p):
+                bag_prob[s] = pool_bags(p, sample_idx[s], pool)
+        elif ok[s]:
+            bag_prob[s] = pool_bags(p, idx_all[s], pool)
+    # np.mean(list of per-pass float32 lists, axis=0): rows are added in pass order, then divided (float32)
+    acc = np.zeros(n_sites, dtype=np.float32)
+    for it in range(n_iters):
+        acc = acc + bag_prob[:, it]
+    return read_prob, bag_prob, (acc / np.float32(n_iters)).astype(np.float32), mod_count

@@ -155,3 +155,54 @@ def sample_indices_mt19937(seed: int, n_reads: int, n_iters: int, n_samples: int
     """
     rs = np.random.RandomState(seed)
     return rs.randint(0, n_reads, size=n_iters * n_samples).reshape(n_iters, n_samples).astype(np.int64)
+
+
+# ---- bags WITHOUT replacement (the validate()-style literal MIL forward) --------------------------------
+# The reference's evaluation datasets draw every bag with
+# ``np.random.choice(len(features), self.min_reads, replace=False)`` (reference
+# m6anet/utils/data_utils.py:213-214), once per site per validation pass
+# (utils/training_utils.py:236-238).  Device specification ("Floyd bags"):
+#
+#   pass `it` of a site uses the same (site, block, lane) MWC64X stream and round as iteration `it` of the
+#   inference stream above, one 32-bit word per draw (no paired regime):
+#       for d in 0 .. k-1:   j = n_reads - k + d
+#                            t = (word_d * (j + 1)) >> 32          uniform on [0, j]
+#                            pick_d = j if t in {pick_0..pick_{d-1}} else t
+#   (R. Floyd's sampling algorithm: the k picks are distinct and every k-subset is equally likely; the order inside
+#    a bag carries no meaning for the pooling functions.)  Sites with n_reads < k have no bag (NaN on the device;
+#    the reference's np.random.choice raises there, and its datasets drop such sites at :129).
+def bag_indices_many(seed: int, site_ids, n_reads, n_iters: int, n_samples: int = 20) -> np.ndarray:
+    """Device without-replacement bags for several sites -> int64 [n_sites, n_iters, n_samples]."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    site_ids = np.asarray(site_ids, dtype=np.uint64).reshape(-1)
+    n_reads = np.asarray(n_reads, dtype=np.int64).reshape(-1)
+    if np.any(n_reads < n_samples):
+        raise ValueError("bag_indices: every site needs at least n_samples reads")
+    S = len(site_ids)
+    ipl, n_blocks = block_layout(n_iters)
+    x, c = _streams(seed, site_ids, n_blocks)
+    A = np.uint64(MWC_A)
+    out = np.empty((S, n_blocks, ipl, 32, n_samples), dtype=np.int64)   # [S, block, round, lane, draw]
+    nr = n_reads[:, None, None]
+    for k in range(ipl):
+        for d in range(n_samples):
+            word = x ^ c
+            t = A * x + c
+            x, c = t & _MASK32, t >> _SHIFT32
+            j = nr - n_samples + d
+            cand = ((word * (j + 1).astype(np.uint64)) >> _SHIFT32).astype(np.int64)
+            dup = (out[:, :, k, :, :d] == cand[..., None]).any(axis=-1) if d else np.zeros(cand.shape, dtype=bool)
+            out[:, :, k, :, d] = np.where(dup, np.broadcast_to(j, cand.shape), cand)
+    return out.reshape(S, n_blocks * ipl * 32, n_samples)[:, :n_iters, :]
+
+
+def bag_indices(seed: int, site_id: int, n_reads: int, n_iters: int, n_samples: int = 20) -> np.ndarray:
+    """Device without-replacement bags of one site -> int64 [n_iters, n_samples], distinct inside a bag."""
+    return bag_indices_many(seed, [int(site_id) & 0xFFFFFFFFFFFFFFFF], [n_reads], n_iters, n_samples)[0]
+
+
+def bag_indices_mt19937(rs: "np.random.RandomState", n_reads: int, n_samples: int = 20) -> np.ndarray:
+    """The bag ``np.random.choice(n_reads, n_samples, replace=False)`` draws from the legacy stream `rs`
+    (reference utils/data_utils.py:214): legacy ``RandomState.choice`` without replacement and without weights is
+    ``permutation(n_reads)[:n_samples]``.  Consumes the stream exactly like the reference call."""
+    return rs.permutation(int(n_reads))[:n_samples].astype(np.int64)

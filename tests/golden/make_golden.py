@@ -24,6 +24,13 @@ Writes
         (MILModel.forward on the gathered [n_iters,20,.] bags, model/model.py:155-164, mean over
         iterations as in utils/training_utils.py:236-256) on the Philox index stream of
         oracle/philox.py; mod_count at the registry threshold.
+  bundled/data.info.labelled, validate_golden.npz
+        the reference's own labelled index, and the outputs of the reference's `validate()`
+        (utils/training_utils.py:213-268) run UNMODIFIED on its 'Val' and 'Test' sets (NanopolishDS mode='Val'/'Test',
+        DataLoader + train_collate, binary_cross_entropy_loss, 5 passes after np.random.seed) for the prod / mean / max
+        pooling blocks: per-pass y_pred, y_true, roc_auc, pr_auc, avg_loss, and the bags the legacy MT19937 stream
+        drew (replayed with oracle.philox.bag_indices_mt19937) so the kernel's explicit-index mode can be held
+        to the very same numbers.
 """
 import gzip
 import json
@@ -194,8 +201,54 @@ def synthetic_outputs(tag, model, threshold, feats, read_off, kmer_idx, extra=No
     print(tag, "p range", float(p.min()), float(p.max()), "site range", float(site.min()), float(site.max()))
 
 
+def validate_golden():
+    from torch.utils.data import DataLoader
+    from m6anet.utils.data_utils import train_collate
+    from m6anet.utils.loss_functions.loss_functions import binary_cross_entropy_loss
+    from m6anet.utils.training_utils import validate
+    from oracle.philox import bag_indices_mt19937
+
+    src = os.path.join(REF, "m6anet", "tests", "data")
+    shutil.copyfile(os.path.join(src, "data.info.labelled"), os.path.join(HERE, "bundled", "data.info.labelled"))
+    name = "HCT116_RNA002"
+    n_iters, seed = 5, 11
+    flat = np.load(os.path.join(HERE, "bundled_flat.npz"))
+    key = {(str(t), int(q)): i for i, (t, q) in enumerate(zip(flat["tx_id"], flat["tx_pos"]))}
+    out = dict(n_iters=n_iters, seed=seed, n_samples=20)
+    base_cfg = toml.load(DEFAULT_MODEL_CONFIG)
+    for pool, block in (("prod", "SigmoidProdPooling"), ("mean", "SigmoidMeanPooling"), ("max", "SigmoidMaxPooling")):
+        cfg = toml.loads(toml.dumps(base_cfg))
+        assert cfg["block"][-1]["block_type"] == "SigmoidProdPooling"
+        cfg["block"][-1]["block_type"] = block
+        model = MILModel(cfg)
+        model.load_state_dict(torch.load(PRETRAINED_CONFIGS[name][0], map_location="cpu"))
+        for mode in ("Val", "Test"):
+            ds = NanopolishDS(src, 20, PRETRAINED_CONFIGS[name][2], mode=mode)
+            dl = DataLoader(ds, batch_size=16, shuffle=False, collate_fn=train_collate)   # num_workers=0: draws in site order
+            np.random.seed(seed)
+            res = validate(model, dl, "cpu", binary_cross_entropy_loss, n_iters)
+            # replay of the legacy stream: one choice(n, 20, replace=False) per site per pass, in loader order
+            rs = np.random.RandomState(seed)
+            n_reads = ds.data_info["n_reads"].values
+            bags = np.stack([np.stack([bag_indices_mt19937(rs, n, 20) for n in n_reads]) for _ in range(n_iters)], axis=1)
+            site_index = np.array([key[(t, int(q))] for t, q in zip(ds.data_info["transcript_id"], ds.data_info["transcript_position"])])
+            tag = f"{pool}_{mode}"
+            out[f"{tag}_y_pred"] = np.asarray(res["y_pred"], dtype=np.float32)       # [n_iters, n_sites]
+            out[f"{tag}_y_true"] = np.asarray(res["y_true"], dtype=np.int64)
+            out[f"{tag}_metrics"] = np.array([res["roc_auc"], res["pr_auc"], res["avg_loss"]], dtype=np.float64)
+            if pool == "prod":
+                out[f"{mode}_site_index"] = site_index.astype(np.int64)              # rows of bundled_flat.npz
+                out[f"{mode}_bags"] = bags.astype(np.uint16)                        # [n_sites, n_iters, 20]
+            print("validate golden", tag, len(ds), "sites", out[f"{tag}_metrics"])
+    np.savez_compressed(os.path.join(HERE, "validate_golden.npz"), **out)
+
+
 def main():
+    if sys.argv[1:] == ["validate"]:
+        validate_golden()
+        return
     bundled()
+    validate_golden()
     replicates()
     feats, read_off, kmer_idx = synthetic_inputs()
     for name, (_, thr, _) in PRETRAINED_CONFIGS.items():
