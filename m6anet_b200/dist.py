@@ -38,6 +38,24 @@ def shard_bounds(n_reads: np.ndarray, world_size: int) -> List[int]:
     return bounds
 
 
+def all_gather_rows(rows, bounds: List[int], group=None):
+    """One all-gather of every rank's per-site rows (float32 [n_local, C]) -> [n_sites, C] on every rank, shards padded
+    to the longest one.  Used for the per-pass predictions of validate() (C = n_iterations)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
+    assert rows.dim() == 2 and rows.shape[0] == sizes[rank] and rows.dtype == torch.float32
+    m, c = max(max(sizes), 1), rows.shape[1]
+    pack = torch.zeros((m, c), dtype=torch.float32, device=rows.device)
+    pack[: sizes[rank]] = rows
+    out = torch.empty((world * m, c), dtype=torch.float32, device=rows.device)
+    dist.all_gather_into_tensor(out, pack, group=group)
+    out = out.view(world, m, c)
+    return torch.cat([out[r, : sizes[r]] for r in range(world)])
+
+
 def all_gather_site_outputs(site_prob, mod_count, bounds: List[int], group=None):
     """One all-gather of every rank's (site_prob, mod_count) -> full-length tensors on every rank.
 

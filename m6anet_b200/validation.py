@@ -13,6 +13,8 @@ drawn and pooled on the device by `m6a_mil_validate_host_f32` (include/m6anet_b2
 (tests/test_validate.py holds the kernel to the outputs of the reference's own validate() on a replayed MT19937
 stream), without n_iterations re-reads of data.json.  The bags come from the counter-based device stream keyed by
 (seed, site index), so the result does not depend on batching or GPU count.  There is no CPU path.
+Under torchrun (WORLD_SIZE > 1) the sites are sharded by read count over the ranks and ONE all-gather of the per-pass
+predictions (4 * n_iterations bytes per site) gives every rank the full matrix; metrics are computed on every rank.
 """
 from __future__ import annotations
 
@@ -175,7 +177,21 @@ def validate(model, val_dl, device: str, criterion: Callable, n_iterations: Opti
     dev = _resolve_device(device, local_rank, world)
     model.eval()
     start = time.time()
-    y_pred = predict_bags(model, ds, dev, int(n_iterations), seed)
+    if world > 1:     # site shards + one all-gather (torch.distributed over NCCL), like run_inference
+        import os
+        import torch
+        import torch.distributed as dist
+        from .dist import all_gather_rows, shard_bounds
+        torch.cuda.set_device(dev)
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+        bounds = shard_bounds(ds.n_reads, world)
+        local = predict_bags(model, ds, dev, int(n_iterations), seed, bounds[rank], bounds[rank + 1])
+        rows = torch.from_numpy(np.ascontiguousarray(local.T)).to(torch.device("cuda", dev))
+        y_pred = np.ascontiguousarray(all_gather_rows(rows, bounds).cpu().numpy().T)
+    else:
+        y_pred = predict_bags(model, ds, dev, int(n_iterations), seed)
     compute_time = time.time() - start
     # np.mean(all_y_pred, axis=0) on the list of per-pass float32 lists: rows added in pass order, float32
     acc = np.zeros(y_pred.shape[1], dtype=np.float32)

@@ -13,7 +13,7 @@ WORKER = textwrap.dedent("""
     import os, sys
     import numpy as np, torch, torch.distributed as dist
     sys.path.insert(0, {root!r})
-    from m6anet_b200.dist import all_gather_site_outputs, env_world, shard_bounds
+    from m6anet_b200.dist import all_gather_rows, all_gather_site_outputs, env_world, shard_bounds
     rank, world, _ = env_world()
     dist.init_process_group("gloo")
     rng = np.random.default_rng(7)
@@ -31,6 +31,12 @@ WORKER = textwrap.dedent("""
     lo, hi = b2[rank], b2[rank + 1]
     sp, mc = all_gather_site_outputs(torch.from_numpy(site_prob[lo:hi].copy()), torch.from_numpy(mod_count[lo:hi].copy()), b2)
     assert np.array_equal(sp.numpy(), site_prob) and np.array_equal(mc.numpy(), mod_count)
+    # per-pass predictions of validate(): [n_local, n_iterations] rows -> the full matrix on every rank
+    y_pred = rng.random((1001, 5)).astype(np.float32)
+    for b in (bounds, b2):
+        lo, hi = b[rank], b[rank + 1]
+        full = all_gather_rows(torch.from_numpy(y_pred[lo:hi].copy()), b)
+        assert full.dtype == torch.float32 and np.array_equal(full.numpy(), y_pred), "y_pred mismatch"
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")
