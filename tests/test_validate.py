@@ -357,7 +357,10 @@ def test_kernel_matches_oracle_on_device_bag_stream(synthetic_inputs, pool, n_sa
                                              n_samples=n_samples, pool=pool)
     assert np.abs(rp - orp).max() <= BAG_ATOL
     assert np.abs(bag_prob - obag).max() <= BAG_ATOL
-    assert np.abs(site_mean - omean).max() <= BAG_ATOL
+    # the device averages the passes pairwise (butterfly over lanes, then blocks): held to the float64 mean of the bags;
+    # the reference-order float32 average (np.mean(all_y_pred, axis=0)) is formed on the host from bag_prob
+    assert np.abs(site_mean - obag.astype(np.float64).mean(axis=1)).max() <= BAG_ATOL
+    assert np.abs(omean - obag.astype(np.float64).mean(axis=1)).max() <= 1e-5
     assert np.abs(mc - omc).max() <= 1
 
 
