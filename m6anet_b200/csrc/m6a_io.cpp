@@ -64,44 +64,116 @@ void fail(IngestCtx& c, int64_t part, int status) {
   if (c.status.compare_exchange_strong(expected, status)) c.bad.store(part);
 }
 
-// Parse one site line: {"tx":{"pos":{"KMER":[[v,...,v],[...]]}}}
+// ---- strict scanner for one site line --------------------------------------------------------------------------
+// The line must be exactly what `m6anet dataprep` writes (reference utils/dataprep_utils.py:473-480) and what the
+// reference reads back with json.loads (utils/data_utils.py:182-189):
+//     {"<tx>":{"<pos>":{"<KMER>":[[v,...,v],[v,...,v],...]}}}   + optional trailing whitespace
+// Anything json.loads would reject is rejected here too (M6A_EPARSE) -- a truncated byte range, a missing bracket, a
+// malformed number -- so a corrupted data.json can not be scored silently.
+inline const char* skip_ws(const char* r, const char* e) {
+  while (r < e && (*r == ' ' || *r == '\t' || *r == '\n' || *r == '\r')) ++r;
+  return r;
+}
+// expects (after whitespace) the character ch; returns the position after it or nullptr
+inline const char* expect(const char* r, const char* e, char ch) {
+  r = skip_ws(r, e);
+  return (r < e && *r == ch) ? r + 1 : nullptr;
+}
+// expects a string without escapes; returns the position after the closing quote, [*s0, *s1) = contents
+inline const char* expect_string(const char* r, const char* e, const char** s0, const char** s1) {
+  r = expect(r, e, '"');
+  if (!r) return nullptr;
+  *s0 = r;
+  for (; r < e && *r != '"'; ++r)
+    if (*r == '\\' || static_cast<unsigned char>(*r) < 0x20) return nullptr;   // escapes never occur in ids / k-mers
+  if (r >= e) return nullptr;
+  *s1 = r;
+  return r + 1;
+}
+// One JSON number (plus the NaN / Infinity / -Infinity literals Python's json writes and reads); nullptr if malformed.
+// Grammar (RFC 8259): -?(0|[1-9][0-9]*)(\.[0-9]+)?([eE][+-]?[0-9]+)?  -- validated while the digits are accumulated.
+// Fast path (W. Clinger): no exponent, at most 19 digits, decimal mantissa w <= 2^53 and at most 22 fraction digits =>
+// w and 10^k are exact doubles and the IEEE division w / 10^k is the correctly rounded value, i.e. what Python's float()
+// returns.  Everything else goes through std::from_chars (correctly rounded as well).
+// The buffer is NUL-terminated at e, so single look-aheads never leave it.
+inline bool is_digit(char ch) { return static_cast<unsigned>(static_cast<unsigned char>(ch) - '0') <= 9u; }
+constexpr double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                               1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+inline const char* parse_number(const char* r, const char* e, double* v) {
+  const bool neg = (*r == '-');
+  const char* d = r + neg;
+  if (!is_digit(*d)) {
+    if (e - r >= 3 && !strncmp(r, "NaN", 3)) { *v = NAN; return r + 3; }
+    if (e - d >= 8 && !strncmp(d, "Infinity", 8)) { *v = neg ? -INFINITY : INFINITY; return d + 8; }
+    return nullptr;
+  }
+  if (*d == '0' && is_digit(d[1])) return nullptr;      // leading zero
+  uint64_t w = 0;
+  const char* q = d;
+  for (; is_digit(*q); ++q) w = w * 10u + static_cast<unsigned>(*q - '0');   // may wrap beyond 19 digits: checked below
+  const char* frac0 = q;
+  if (*q == '.') {
+    ++q;
+    frac0 = q;
+    if (!is_digit(*q)) return nullptr;                   // "1." / "1.e5"
+    for (; is_digit(*q); ++q) w = w * 10u + static_cast<unsigned>(*q - '0');
+  }
+  const int n_frac = static_cast<int>(q - frac0);
+  const bool has_exp = (*q == 'e' || *q == 'E');
+  if (!has_exp && (q - d) <= 19 && w <= (1ull << 53) && n_frac <= 22) {   // (q - d) <= 19 characters: w did not wrap
+    const double x = static_cast<double>(w) / kPow10[n_frac];
+    *v = neg ? -x : x;
+    return q;
+  }
+  if (has_exp) {                                          // [eE][+-]?[0-9]+
+    const char* x = q + 1;
+    if (*x == '+' || *x == '-') ++x;
+    if (!is_digit(*x)) return nullptr;
+  }
+  const auto res = std::from_chars(r, e, *v);
+  // out of range: json.loads gives +-inf / 0.0 there; dataprep never writes such values, so refuse rather than guess
+  if (res.ec != std::errc()) return nullptr;
+  return res.ptr;
+}
+// whitespace is legal JSON between tokens but dataprep writes none: test before calling
+inline const char* ws(const char* r, const char* e) {
+  return static_cast<unsigned char>(*r) <= ' ' ? skip_ws(r, e) : r;
+}
+
 bool parse_part(IngestCtx& c, int64_t pi, std::vector<char>& buf) {
   const m6a_part_t& p = c.parts[pi];
   const int64_t len = p.end - p.start;
-  if (len <= 0 || p.file < 0) return false;
+  if (len <= 0 || p.file < 0 || p.n_rows < 0) return false;
   buf.resize(static_cast<size_t>(len) + 1);
   int64_t got = 0;
   while (got < len) {
     const ssize_t r = pread(c.fds[p.file], buf.data() + got, static_cast<size_t>(len - got), p.start + got);
-    if (r <= 0) {
+    if (r < 0) {
       fail(c, pi, M6A_EIO);
       return true;  // status already set
     }
+    if (r == 0) return false;   // the byte range runs past the end of the file: data.info does not match data.json
     got += r;
   }
   buf[len] = 0;
-  const char* s = buf.data();
-  const char* e = s + len;
-  // the third '{' opens {"KMER":[[...
-  int braces = 0;
-  const char* q = s;
-  for (; q < e; ++q) {
-    if (*q == '"') {  // skip strings
-      for (++q; q < e && *q != '"'; ++q) {}
-      continue;
-    }
-    if (*q == '{' && ++braces == 3) break;
-  }
-  if (q >= e) return false;
-  const char* k0 = static_cast<const char*>(memchr(q, '"', e - q));
-  if (!k0) return false;
-  ++k0;
-  const char* k1 = static_cast<const char*>(memchr(k0, '"', e - k0));
-  if (!k1) return false;
+  const char* e = buf.data() + len;
+  // {"tx":{"pos":{"KMER":[
+  const char *t0, *t1, *k0, *k1;
+  const char* r = expect(buf.data(), e, '{');
+  if (r) r = expect_string(r, e, &t0, &t1);
+  if (r) r = expect(r, e, ':');
+  if (r) r = expect(r, e, '{');
+  if (r) r = expect_string(r, e, &t0, &t1);
+  if (r) r = expect(r, e, ':');
+  if (r) r = expect(r, e, '{');
+  if (r) r = expect_string(r, e, &k0, &k1);
+  if (r) r = expect(r, e, ':');
+  if (r) r = expect(r, e, '[');
+  if (!r) return false;
   const int klen = static_cast<int>(k1 - k0);
   if (klen < 5 || ((klen - 5) & 1)) return false;
   const int T = (klen - 5) / 2, n = c.n_flank;       // flanks in the file / wanted
-  if (n > T) return false;
+  if (n > T || T > 5) return false;
   const int n_pos = 2 * n + 1, n_sig = 3 * n_pos, row_w = 3 * (2 * T + 1) + 1;
   // five-mers of the centred (5+2n)-mer, normalisation vectors, ids
   double mean[33], stdv[33];
@@ -116,44 +188,50 @@ bool parse_part(IngestCtx& c, int64_t pi, std::vector<char>& buf) {
       if (std::isnan(mean[3 * j + i]) || std::isnan(stdv[3 * j + i])) return false;   // k-mer missing from norm factors
     }
   }
-  int32_t* kid = c.kmer_idx + p.site * n_pos;
-  if (p.first_of_site) {
-    for (int j = 0; j < n_pos; ++j) kid[j] = ids[j];
-  }
   const int col0 = (T - n) * 3;   // selected signal columns are contiguous: [(T-n)*3, (T+n+1)*3)
-  // rows
-  const char* r = k1 + 1;
+  // rows: [v,...,v] separated by ',' and closed by ']'
   double vals[40];
   int64_t row = 0;
-  while (r < e) {
-    // find next '[' that starts a row (skip the outer one)
-    while (r < e && *r != '[' && *r != '}') ++r;
-    if (r >= e || *r == '}') break;
-    ++r;
-    if (r < e && *r == '[') continue;   // outer bracket: next loop iteration finds the inner one
-    if (r < e && *r == ']') break;      // empty list
-    int nv = 0;
-    while (r < e) {
-      while (r < e && (*r == ' ' || *r == ',')) ++r;
-      if (r < e && *r == ']') { ++r; break; }
-      if (nv >= 40) return false;
-      double v;
-      auto res = std::from_chars(r, e, v);
-      if (res.ec != std::errc()) {
-        if (e - r >= 3 && !strncmp(r, "NaN", 3)) { v = NAN; res.ptr = r + 3; }
-        else return false;
+  r = skip_ws(r, e);
+  if (r < e && *r == ']') {
+    ++r;                                  // empty list
+  } else {
+    for (;;) {
+      r = expect(r, e, '[');
+      if (!r) return false;
+      int nv = 0;
+      for (;;) {
+        r = ws(r, e);
+        if (nv >= 40 || r >= e) return false;
+        r = parse_number(r, e, &vals[nv]);
+        if (!r) return false;
+        ++nv;
+        r = ws(r, e);
+        if (*r == ',') { ++r; continue; }      // (*e == 0: running off the end fails the three tests)
+        if (*r == ']') { ++r; break; }
+        return false;
       }
-      vals[nv++] = v;
-      r = res.ptr;
+      if (nv != row_w || row >= p.n_rows) return false;
+      float* out = c.feats + (p.row_off + row) * n_sig;
+      for (int k = 0; k < n_sig; ++k) out[k] = static_cast<float>((vals[col0 + k] - mean[k]) / stdv[k]);
+      c.read_ids[p.row_off + row] = static_cast<int64_t>(vals[row_w - 1]);
+      ++row;
+      r = skip_ws(r, e);
+      if (r >= e) return false;
+      if (*r == ',') { ++r; continue; }
+      if (*r == ']') { ++r; break; }
+      return false;
     }
-    if (nv != row_w) return false;
-    if (row >= p.n_rows) return false;
-    float* out = c.feats + (p.row_off + row) * n_sig;
-    for (int k = 0; k < n_sig; ++k) out[k] = static_cast<float>((vals[col0 + k] - mean[k]) / stdv[k]);
-    c.read_ids[p.row_off + row] = static_cast<int64_t>(vals[row_w - 1]);
-    ++row;
   }
-  return row == p.n_rows;
+  // }}} and nothing but whitespace up to the end of the byte range
+  for (int k = 0; k < 3 && r; ++k) r = expect(r, e, '}');
+  if (!r || skip_ws(r, e) != e) return false;
+  if (row != p.n_rows) return false;
+  if (p.first_of_site) {
+    int32_t* kid = c.kmer_idx + p.site * n_pos;
+    for (int j = 0; j < n_pos; ++j) kid[j] = ids[j];
+  }
+  return true;
 }
 
 void ingest_worker(IngestCtx* c) {

@@ -333,3 +333,114 @@ def test_native_info_reader_matches_pandas(bundled_dir, tmp_path):
     assert len(read_info(str(d))[0]) == 0
     with pytest.raises(M6AError):
         read_info(str(tmp_path / "missing"))
+
+
+def test_native_number_parser_is_correctly_rounded_and_strict(tmp_path):
+    """m6a_ingest_parts parses numbers either on a Clinger fast path (mantissa <= 2^53, <= 22 fraction digits: one exact
+    division) or with std::from_chars.  Both must give Python's float() to the last bit: the norm tables are set to
+    mean = float(text), std = ulp, so any difference shows up as a non-zero feature.  Malformed numbers and malformed
+    lines (anything json.loads rejects) must be refused with M6A_EPARSE."""
+    import ctypes as C
+    import json
+    from m6anet_b200 import _cabi
+    L = _cabi.lib()
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    enc = lambda k: sum(code[ch] * 4 ** (4 - i) for i, ch in enumerate(k))
+    codes = [enc(k) for k in ("AGGAC", "GGACT", "GACTG")]
+    kid = np.full(1024, -1, dtype=np.int32)
+    kid[codes] = [0, 1, 2]
+    path = tmp_path / "n.json"
+    paths = (C.c_char_p * 1)(os.fsencode(str(path)))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def ingest(line: str, n_rows=1, mean=None, std=None):
+        path.write_text(line)
+        parts = np.zeros(1, dtype=_cabi.PART_DTYPE)
+        parts[0] = (0, 0, 0, len(line.encode()), 0, n_rows, 0, 1, 0)
+        m = np.zeros((1024, 3)) if mean is None else mean
+        s = np.ones((1024, 3)) if std is None else std
+        feats = np.full((max(n_rows, 1), 9), 99.0, dtype=np.float32)
+        ids = np.zeros(max(n_rows, 1), dtype=np.int64)
+        kmer = np.zeros((1, 3), dtype=np.int32)
+        bad = C.c_int64(-1)
+        rc = L.m6a_ingest_parts(paths, 1, vp(parts), 1, 1, vp(np.ascontiguousarray(m)), vp(np.ascontiguousarray(s)), vp(kid),
+                                vp(feats), vp(ids), vp(kmer), 1, C.byref(bad))
+        return rc, feats, ids
+
+    rng = np.random.default_rng(11)
+
+    def random_decimal():
+        kind = rng.integers(0, 6)
+        if kind == 0:        # fast path: short mantissa, a few fraction digits (what dataprep writes after rounding)
+            return "%d.%0*d" % (rng.integers(0, 10**4), int(rng.integers(1, 8)), rng.integers(0, 10**6) % 10 ** int(rng.integers(1, 7)))
+        if kind == 1:        # repr of a double: 15-17 significant digits, both sides of the 2^53 mantissa limit
+            return repr(float(rng.normal(0, 1) * 10.0 ** int(rng.integers(-8, 8))))
+        if kind == 2:        # mantissa around 2^53 with a random number of fraction digits
+            w = (1 << 53) + int(rng.integers(-3, 4))
+            t = str(w)
+            k = int(rng.integers(0, 16))
+            return t[:len(t) - k] + "." + t[len(t) - k:] if k else t
+        if kind == 3:        # many leading zeros in the fraction (up to and beyond 22 fraction digits)
+            return "0." + "0" * int(rng.integers(0, 24)) + str(rng.integers(1, 10**5))
+        if kind == 4:        # exponents
+            return "%.*e" % (int(rng.integers(0, 17)), rng.normal(0, 1) * 10.0 ** int(rng.integers(-30, 30)))
+        return str(int(rng.integers(-10**15, 10**15)))            # integers
+
+    for _ in range(300):
+        texts = [("-" if rng.random() < 0.3 and not t.startswith("-") else "") + t for t in (random_decimal() for _ in range(9))]
+        want = np.array([float(t) for t in texts])
+        mean = np.zeros((1024, 3))
+        std = np.ones((1024, 3))
+        for j, c in enumerate(codes):
+            mean[c] = want[3 * j:3 * j + 3]
+            std[c] = np.maximum(np.spacing(np.abs(want[3 * j:3 * j + 3])), 5e-324)
+        line = '{"t":{"1":{"AGGACTG":[[%s,12345.0]]}}}\n' % ",".join(texts)
+        assert json.loads(line)
+        rc, feats, ids = ingest(line, 1, mean, std)
+        assert rc == 0, (rc, line)
+        assert np.array_equal(feats[0], np.zeros(9, dtype=np.float32)), (texts, feats[0])    # 0 ulp from float(text)
+        assert ids[0] == 12345
+
+    good_row = "[" + ",".join(["1.5"] * 9) + ",7.0]"
+    ok = '{"t":{"1":{"AGGACTG":[%s]}}}\n' % good_row
+    assert ingest(ok)[0] == 0
+    assert ingest(' { "t" : { "1" : { "AGGACTG" : [ [ %s , 7.0 ] ] } } } \n' % " , ".join(["1.5"] * 9))[0] == 0   # JSON whitespace
+    for bad_number in ("01.5", "1.", ".5", "+1.5", "1.5.2", "1e", "1e+", "0x10", "nan", "inf", "1,5", "--1", "1e400", ""):
+        line = ok.replace("1.5", bad_number, 1)
+        with pytest.raises(ValueError):
+            v = json.loads(line)                 # json.loads rejects all of these, or (1e400) gives inf ...
+            if bad_number in ("1e400", "1,5"):   # ... or a different row width: refused as well
+                raise ValueError
+        assert ingest(line)[0] == -6, bad_number
+    for broken in (ok[:-2] + "\n",                       # a closing brace missing
+                   ok.rstrip("\n")[:-3],                # truncated after the list
+                   ok.replace("]}}}", "}}}"),           # outer list not closed
+                   ok.replace("[[", "["),               # rows not nested
+                   ok.replace('"AGGACTG":', '"AGGACTG"'),
+                   ok.replace("7.0]", "7.0"),           # row not closed (cut inside the byte range)
+                   ok.rstrip("\n") + "x\n",            # trailing garbage inside the byte range
+                   ok.replace("1.5,", "1.5,,", 1),
+                   ok.replace('"t"', '"t\\"x"')):       # escapes never occur in transcript ids
+        assert ingest(broken)[0] == -6, broken
+    assert ingest(ok, n_rows=2)[0] == -6 and ingest(ok, n_rows=0)[0] == -6           # row count must match data.info
+    # byte range past the end of the file: data.info does not belong to this data.json
+    path.write_text(ok)
+    parts = np.zeros(1, dtype=_cabi.PART_DTYPE)
+    parts[0] = (0, 0, 0, len(ok) + 10, 0, 1, 0, 1, 0)
+    feats, ids, kmer = np.zeros((1, 9), np.float32), np.zeros(1, np.int64), np.zeros((1, 3), np.int32)
+    bad = C.c_int64(-1)
+    z, o = np.zeros((1024, 3)), np.ones((1024, 3))
+    assert L.m6a_ingest_parts(paths, 1, vp(parts), 1, 1, vp(z), vp(o), vp(kid), vp(feats), vp(ids), vp(kmer), 1, C.byref(bad)) == -6
+    assert bad.value == 0
+
+
+def test_ingest_fuzz_accepts_only_what_json_accepts():
+    """tools/fuzz_ingest.py: corrupted site lines / part tables are either refused with a status or parsed to exactly
+    what json.loads gives; never a crash or a write outside the output window (guard bands)."""
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("fuzz_ingest", os.path.join(ROOT, "tools", "fuzz_ingest.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    stats = mod.run(250, seed=3, verbose=False)
+    assert stats["ok"] + stats["rejected"] == 250 and stats["rejected"] > 100 and stats["ok"] > 0
