@@ -7,10 +7,14 @@
 // rounded once to float32, so the buffers equal the reference's NanopolishDS output bit for bit.
 #include <fcntl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <charconv>
 #include <cmath>
 #include <string>
@@ -261,19 +265,71 @@ bool write_all(int fd, const char* p, size_t n) {
   return true;
 }
 
+// Growable output buffer without zero-fill (std::string::resize would touch every byte twice).
+struct OutBuf {
+  char* p = nullptr;
+  size_t len = 0, cap = 0;
+  ~OutBuf() { free(p); }
+  bool ensure(size_t extra) {          // room for `extra` more bytes
+    if (len + extra <= cap) return true;
+    size_t want = cap ? cap * 2 : (1u << 16);
+    while (want < len + extra) want *= 2;
+    char* q = static_cast<char*>(realloc(p, want));
+    if (!q) return false;
+    p = q;
+    cap = want;
+    return true;
+  }
+  void append(const char* src, size_t n) {
+    memcpy(p + len, src, n);
+    len += n;
+  }
+};
+
+// Sites are cut into chunks (a few per worker); workers format chunks into private buffers, the calling thread writes
+// them to fd in site order as they complete, so formatting overlaps the write() copies.  format_range(a, b, out) returns
+// false when it ran out of memory.
 template <class F>
 int format_parallel(int fd, int64_t n_sites, int32_t n_threads, F&& format_range) {
   const int nw = n_workers(n_threads, n_sites);
-  std::vector<std::string> out(nw);
+  const int64_t n_chunks = std::min<int64_t>(n_sites, static_cast<int64_t>(nw) * 4);
+  std::vector<OutBuf> out(static_cast<size_t>(n_chunks));
+  std::vector<int> state(static_cast<size_t>(n_chunks), 0);      // 0 pending, 1 done, -1 failed (guarded by mu)
+  std::mutex mu;
+  std::condition_variable cv;
+  std::atomic<int64_t> next{0};
+  std::atomic<bool> stop{false};
   std::vector<std::thread> th;
-  for (int t = 0; t < nw; ++t) {
-    const int64_t a = n_sites * t / nw, b = n_sites * (t + 1) / nw;
-    th.emplace_back([&, t, a, b] { format_range(a, b, out[t]); });
-  }
-  for (auto& x : th) x.join();
   for (int t = 0; t < nw; ++t)
-    if (!write_all(fd, out[t].data(), out[t].size())) return M6A_EIO;
-  return M6A_OK;
+    th.emplace_back([&] {
+      for (;;) {
+        const int64_t c = next.fetch_add(1);
+        if (c >= n_chunks || stop.load()) return;
+        const int64_t a = n_sites * c / n_chunks, b = n_sites * (c + 1) / n_chunks;
+        const bool ok = format_range(a, b, out[static_cast<size_t>(c)]);
+        {
+          std::lock_guard<std::mutex> g(mu);
+          state[static_cast<size_t>(c)] = ok ? 1 : -1;
+        }
+        cv.notify_all();
+      }
+    });
+  int rc = M6A_OK;
+  for (int64_t c = 0; c < n_chunks && rc == M6A_OK; ++c) {
+    {
+      std::unique_lock<std::mutex> g(mu);
+      cv.wait(g, [&] { return state[static_cast<size_t>(c)] != 0; });
+      if (state[static_cast<size_t>(c)] < 0) rc = M6A_ENOMEM;
+    }
+    OutBuf& o = out[static_cast<size_t>(c)];
+    if (rc == M6A_OK && !write_all(fd, o.p, o.len)) rc = M6A_EIO;
+    free(o.p);                                                     // release as soon as written
+    o.p = nullptr;
+    o.len = o.cap = 0;
+  }
+  stop.store(true);
+  for (auto& x : th) x.join();
+  return rc;
 }
 
 }  // namespace
@@ -454,24 +510,101 @@ extern "C" int m6a_info_read(const char* path, int64_t n_rows, int64_t tx_bytes,
   return row == n_rows ? M6A_OK : M6A_EPARSE;
 }
 
-// '%s,%d,%s,%.16f,%s,%.16f\n' % (tx_id, tx_pos, n_read, site_prob, kmer, mod_ratio)   utils/inference_utils.py:59-60
+// ---- exact fast formatting --------------------------------------------------------------------------------------
+// "%.16f" of a double in [0, 1] -- every probability and ratio of the two CSV files -- exactly as printf / Python's '%'
+// print it (round-half-even on the exact binary value), without the multi-precision machinery of printf:
+// p = m * 2^-k with m < 2^53, so p * 10^16 = m * 10^16 / 2^k needs 107 bits: one 128-bit product, one shift, one
+// comparison of the remainder with the half.  Returns the number of characters written (18), or 0 if p is outside
+// [0, 1] or not finite (the caller then falls back to snprintf).
+static const char kDigitPairs[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960"
+    "616263646566676869707172737475767778798081828384858687888990919293949596979899";
+
+inline int format_prob16(double p, char* out) {
+  uint64_t bits;
+  memcpy(&bits, &p, sizeof bits);
+  if (bits > 0x3FF0000000000000ull) return 0;        // negative (sign bit), > 1, inf or NaN
+  const int be = static_cast<int>(bits >> 52);
+  uint64_t m = bits & ((1ull << 52) - 1);
+  int k;                                               // p = m * 2^-k, k >= 52
+  if (be == 0) {
+    k = 1074;
+  } else {
+    m |= 1ull << 52;
+    k = 1075 - be;
+  }
+  uint64_t q = 0;                                      // round(p * 10^16), <= 10^16
+  if (k < 128) {
+    const unsigned __int128 num = static_cast<unsigned __int128>(m) * 10000000000000000ull;   // < 2^107
+    q = static_cast<uint64_t>(num >> k);
+    const unsigned __int128 rem = num & ((static_cast<unsigned __int128>(1) << k) - 1);
+    const unsigned __int128 half = static_cast<unsigned __int128>(1) << (k - 1);
+    if (rem > half || (rem == half && (q & 1u))) ++q;
+  }                                                    // k >= 128: num < 2^107 < half => 0
+  const uint64_t ip = q / 10000000000000000ull;        // 0 or 1
+  uint64_t frac = q - ip * 10000000000000000ull;
+  out[0] = static_cast<char>('0' + ip);
+  out[1] = '.';
+  for (int i = 7; i >= 0; --i) {                       // 16 digits, two at a time from the right
+    const uint64_t d = frac % 100;
+    frac /= 100;
+    out[2 + 2 * i] = kDigitPairs[2 * d];
+    out[3 + 2 * i] = kDigitPairs[2 * d + 1];
+  }
+  return 18;
+}
+
+inline int format_prob16_or_printf(double p, char* out) {     // out holds >= 400 bytes ("%.16f" of DBL_MAX is 326 long)
+  const int n = format_prob16(p, out);
+  return n ? n : snprintf(out, 400, "%.16f", p);
+}
+
+inline int format_i64(long long v, char* out) {              // "%lld"
+  char tmp[24];
+  unsigned long long u = v < 0 ? 0ull - static_cast<unsigned long long>(v) : static_cast<unsigned long long>(v);
+  int n = 0;
+  do {
+    tmp[n++] = static_cast<char>('0' + u % 10);
+    u /= 10;
+  } while (u);
+  int w = 0;
+  if (v < 0) out[w++] = '-';
+  while (n) out[w++] = tmp[--n];
+  return w;
+}
+
+// '%s,%d,%s,%.16f,%s,%.16f\n' % (tx_id, tx_pos, n_reads, site_prob, kmer, mod_ratio)   utils/inference_utils.py:59-60
 extern "C" int m6a_write_site_csv(int32_t fd, int64_t n_sites, const char* tx_buf, const int64_t* tx_off,
                                   const int64_t* tx_pos, const int64_t* read_off, const float* site_prob,
                                   const int32_t* mod_count, const char* kmer5, int32_t n_threads) {
   if (n_sites < 0) return M6A_EINVAL;
   if (n_sites == 0) return M6A_OK;
   if (!tx_buf || !tx_off || !tx_pos || !read_off || !site_prob || !mod_count || !kmer5) return M6A_EINVAL;
-  return format_parallel(fd, n_sites, n_threads, [&](int64_t a, int64_t b, std::string& out) {
-    char line[160];
-    out.reserve(static_cast<size_t>(b - a) * 96);
+  return format_parallel(fd, n_sites, n_threads, [&](int64_t a, int64_t b, OutBuf& out) {
+    char line[1024];
     for (int64_t s = a; s < b; ++s) {
       const int64_t n = read_off[s + 1] - read_off[s];
       const double ratio = static_cast<double>(mod_count[s]) / static_cast<double>(n > 0 ? n : 1);
-      out.append(tx_buf + tx_off[s], static_cast<size_t>(tx_off[s + 1] - tx_off[s]));
-      const int m = snprintf(line, sizeof line, ",%lld,%lld,%.16f,%.5s,%.16f\n", static_cast<long long>(tx_pos[s]),
-                             static_cast<long long>(n), static_cast<double>(site_prob[s]), kmer5 + 5 * s, ratio);
-      out.append(line, static_cast<size_t>(m));
+      const size_t tl = static_cast<size_t>(tx_off[s + 1] - tx_off[s]);
+      if (!out.ensure(tl + sizeof line)) return false;
+      out.append(tx_buf + tx_off[s], tl);
+      char* w = line;
+      *w++ = ',';
+      w += format_i64(tx_pos[s], w);
+      *w++ = ',';
+      w += format_i64(n, w);
+      *w++ = ',';
+      w += format_prob16_or_printf(static_cast<double>(site_prob[s]), w);     // "nan" for a site without reads
+      *w++ = ',';
+      const size_t kl = strnlen(kmer5 + 5 * s, 5);                             // "%.5s"
+      memcpy(w, kmer5 + 5 * s, kl);
+      w += kl;
+      *w++ = ',';
+      w += format_prob16_or_printf(ratio, w);
+      *w++ = '\n';
+      out.append(line, static_cast<size_t>(w - line));
     }
+    return true;
   });
 }
 
@@ -483,25 +616,34 @@ extern "C" int m6a_write_indiv_csv(int32_t fd, int64_t n_sites, const char* tx_b
   if (n_sites < 0) return M6A_EINVAL;
   if (n_sites == 0) return M6A_OK;
   if (!tx_buf || !tx_off || !tx_pos || !read_off || !read_ids || !read_prob) return M6A_EINVAL;
-  return format_parallel(fd, n_sites, n_threads, [&](int64_t a, int64_t b, std::string& out) {
-    char line[128];
-    out.reserve(static_cast<size_t>(read_off[b] - read_off[a]) * 64);
+  return format_parallel(fd, n_sites, n_threads, [&](int64_t a, int64_t b, OutBuf& out) {
+    // rows are formatted in place behind the site prefix "tx,pos,": a row adds at most 20 + 1 + 11 + 1 + 400 + 1 bytes
+    std::string prefix;
     for (int64_t s = a; s < b; ++s) {
-      const char* tx = tx_buf + tx_off[s];
-      const size_t tl = static_cast<size_t>(tx_off[s + 1] - tx_off[s]);
       char pos[32];
-      const int pl = snprintf(pos, sizeof pos, ",%lld,", static_cast<long long>(tx_pos[s]));
+      int pl = 0;
+      pos[pl++] = ',';
+      pl += format_i64(tx_pos[s], pos + pl);
+      pos[pl++] = ',';
+      prefix.assign(tx_buf + tx_off[s], static_cast<size_t>(tx_off[s + 1] - tx_off[s]));
+      prefix.append(pos, static_cast<size_t>(pl));
+      const size_t row_max = prefix.size() + 440;
       for (int64_t r = read_off[s]; r < read_off[s + 1]; ++r) {
-        out.append(tx, tl);
-        out.append(pos, static_cast<size_t>(pl));
-        int m;
-        if (read_rep)
-          m = snprintf(line, sizeof line, "%lld_%d,%.16f\n", static_cast<long long>(read_ids[r]), read_rep[r],
-                       static_cast<double>(read_prob[r]));
-        else
-          m = snprintf(line, sizeof line, "%lld,%.16f\n", static_cast<long long>(read_ids[r]), static_cast<double>(read_prob[r]));
-        out.append(line, static_cast<size_t>(m));
+        if (out.cap - out.len < row_max && !out.ensure(row_max)) return false;
+        char* w = out.p + out.len;
+        memcpy(w, prefix.data(), prefix.size());
+        w += prefix.size();
+        w += format_i64(read_ids[r], w);
+        if (read_rep) {
+          *w++ = '_';
+          w += format_i64(read_rep[r], w);
+        }
+        *w++ = ',';
+        w += format_prob16_or_printf(static_cast<double>(read_prob[r]), w);     // printf spelling only for NaN / p outside [0, 1]
+        *w++ = '\n';
+        out.len = static_cast<size_t>(w - out.p);
       }
     }
+    return true;
   });
 }

@@ -331,7 +331,7 @@ class NanopolishDS:
             raise _cabi.M6AError(rc, "m6a_ingest_parts" + where)
         read_off = np.zeros(S + 1, dtype=np.int64)
         read_off[1:] = row_off[1:][np.cumsum(counts) - 1] if S and (b - a) else 0
-        centre = np.array([self.int_to_kmer[int(k)] for k in kmer_idx[:, n_pos // 2]]) if S else np.array([], dtype=str)
+        centre = np.asarray(self.all_kmers)[kmer_idx[:, n_pos // 2]] if S else np.array([], dtype=str)    # == int_to_kmer
         rep = np.repeat(self._part_rep[a:b], rows).astype(np.int32) if self._multi else None
         return SiteBatch(feats=feats, read_off=read_off, kmer_idx=kmer_idx, read_ids=read_ids,
                          tx_ids=self._tx_bytes[lo:hi].astype(str),

@@ -70,11 +70,23 @@ def argparser():
 
 
 # ---- CSV emit (native, multi-threaded: m6a_write_site_csv / m6a_write_indiv_csv) -------------------------
-def _tx_buffer(tx_ids: np.ndarray):
-    enc = [str(t).encode("utf-8") for t in tx_ids]
-    off = np.zeros(len(enc) + 1, dtype=np.int64)
-    np.cumsum([len(e) for e in enc], out=off[1:])
-    return b"".join(enc), off
+def _tx_buffer(batch: SiteBatch):
+    """(concatenated utf-8 transcript ids, CSR offsets [S+1]) of a batch, vectorised and cached on the batch
+    (both writers need it; a per-site Python loop costs ~2 us per site)."""
+    cached = getattr(batch, "_tx_buffer", None)
+    if cached is not None:
+        return cached
+    ids = np.asarray(batch.tx_ids)
+    if ids.dtype.kind != "S":
+        ids = np.char.encode(ids.astype(str), "utf-8") if len(ids) else np.zeros(0, dtype="S1")
+    width = max(ids.dtype.itemsize, 1)
+    lengths = np.char.str_len(ids).astype(np.int64) if len(ids) else np.zeros(0, dtype=np.int64)
+    mat = np.ascontiguousarray(ids).view(np.uint8).reshape(len(ids), width) if len(ids) else np.zeros((0, 1), np.uint8)
+    buf = mat[np.arange(width)[None, :] < lengths[:, None]].tobytes()        # row-major => ids in site order
+    off = np.zeros(len(ids) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=off[1:])
+    batch._tx_buffer = (buf, off)
+    return batch._tx_buffer
 
 
 def _vp(a):
@@ -87,8 +99,8 @@ def write_site_rows(f, batch: SiteBatch, site_prob: np.ndarray, mod_count: np.nd
     mod_ratio = mod_count / n_reads in float64 == np.mean(p >= thr) (reference utils/inference_utils.py:53,59-60)."""
     from . import _cabi
     f.flush()
-    tx, off = _tx_buffer(batch.tx_ids)
-    kmer5 = "".join(str(k)[:5].ljust(5) for k in batch.kmers).encode("ascii")
+    tx, off = _tx_buffer(batch)
+    kmer5 = np.asarray(batch.kmers).astype("S5").tobytes() if batch.n_sites else b""     # [S, 5] chars, NUL padded
     pos = np.ascontiguousarray(batch.tx_pos, dtype=np.int64)
     ro = np.ascontiguousarray(batch.read_off, dtype=np.int64)
     sp = np.ascontiguousarray(site_prob, dtype=np.float32)
@@ -102,7 +114,7 @@ def write_indiv_rows(g, batch: SiteBatch, read_prob: np.ndarray, n_threads: int 
     read_index is the integer id, or "{id}_{replicate}" for multi-directory input (utils/data_utils.py:421-423)."""
     from . import _cabi
     g.flush()
-    tx, off = _tx_buffer(batch.tx_ids)
+    tx, off = _tx_buffer(batch)
     pos = np.ascontiguousarray(batch.tx_pos, dtype=np.int64)
     ro = np.ascontiguousarray(batch.read_off, dtype=np.int64)
     ids = np.ascontiguousarray(batch.read_ids, dtype=np.int64)

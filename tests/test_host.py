@@ -157,6 +157,53 @@ def test_csv_row_formats_match_reference(bundled_flat):
     assert fl == want_f and gl == want_g
 
 
+def test_csv_probability_formatting_is_exact():
+    """The writers format '%.16f' with an exact 128-bit integer path for values in [0, 1] (round-half-even on the binary
+    value, like printf / Python) and fall back to printf otherwise.  Checked against Python's '%' on the cases that break
+    approximate formatters: exact ties at the 17th decimal (odd m / 2^17), powers of two, float32 denormals, values just
+    below 1, every ratio count / n, NaN, negative and > 1 values, negative positions and ids."""
+    import tempfile
+    from m6anet_b200.data import SiteBatch
+    from m6anet_b200.inference import write_indiv_rows, write_site_rows
+    rng = np.random.default_rng(4)
+    ties = (np.arange(1, 4001, 2, dtype=np.float64) / 2.0 ** 17).astype(np.float32)               # x * 1e16 ends in .5 exactly
+    pow2 = (2.0 ** -np.arange(0, 150, dtype=np.float64)).astype(np.float32)                       # down into the denormals
+    near1 = np.nextafter(np.float32(1), np.float32(0)) - np.arange(50, dtype=np.float32) * np.float32(6e-8)
+    bits = rng.integers(0, 0x3F800000, 20000, dtype=np.int64).astype(np.uint32).view(np.float32)  # uniform over bit patterns
+    special = np.array([0.0, 1.0, np.nan, -0.25, 1.5, np.inf, -np.inf, 1e-45, 3.4e38, -0.0], dtype=np.float32)
+    rp = np.concatenate([ties, pow2, near1, bits, special]).astype(np.float32)
+    R = len(rp)
+    n = np.full(R // 10, 10)
+    n[-1] += R - n.sum()
+    S = len(n)
+    off = np.concatenate([[0], np.cumsum(n)])
+    ids = rng.integers(-10**6, 10**12, R)
+    batch = SiteBatch(np.zeros((R, 9), np.float32), off, np.zeros((S, 3), np.int32), ids,
+                      np.array([f"tx{i}" for i in range(S)]), rng.integers(-5, 10**9, S), np.array(["GGACT"] * S))
+    with tempfile.TemporaryFile("w+b") as g:
+        write_indiv_rows(g, batch, rp, n_threads=3)
+        g.seek(0)
+        got = g.read().decode()
+    want = "".join('%s,%d,%s,%.16f\n' % (t, p, r, float(a)) for t, p, r, a in
+                   zip(np.repeat(batch.tx_ids, n), np.repeat(batch.tx_pos, n), ids, rp))
+    assert got == want
+    # mod_ratio: every count / n up to 120 reads (doubles with full 53-bit mantissas), site probabilities incl. NaN
+    pairs = [(c, k) for k in range(1, 121) for c in range(k + 1)]
+    S = len(pairs)
+    k_arr = np.array([k for _, k in pairs])
+    off = np.concatenate([[0], np.cumsum(k_arr)])
+    sp = np.resize(np.concatenate([rp[:5000], special]), S).astype(np.float32)
+    batch = SiteBatch(np.zeros((off[-1], 9), np.float32), off, np.zeros((S, 3), np.int32), np.zeros(off[-1], np.int64),
+                      np.array([f"tx{i}" for i in range(S)]), np.arange(S), np.array(["GGACT"] * S))
+    with tempfile.TemporaryFile("w+b") as f:
+        write_site_rows(f, batch, sp, np.array([c for c, _ in pairs], np.int32), n_threads=2)
+        f.seek(0)
+        got = f.read().decode()
+    want = "".join('%s,%d,%s,%.16f,%s,%.16f\n' % (f"tx{i}", i, k, float(a), "GGACT", c / k)
+                   for i, ((c, k), a) in enumerate(zip(pairs, sp)))
+    assert got == want
+
+
 def test_argparser_keeps_reference_flags():
     from m6anet_b200 import constants as C
     from m6anet_b200.inference import argparser
