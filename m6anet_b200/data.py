@@ -43,6 +43,7 @@ class SiteBatch:
     tx_pos: np.ndarray       # [S] int64
     kmers: np.ndarray        # [S] centre 5-mer (str)
     read_rep: Optional[np.ndarray] = None   # [R] int32 replicate number (multi-directory input) -> "{id}_{rep}"
+    tx_bytes: Optional[np.ndarray] = None   # [S] fixed-width bytes view of tx_ids (what the CSV writers consume)
 
     @property
     def n_sites(self) -> int:
@@ -335,7 +336,7 @@ class NanopolishDS:
         rep = np.repeat(self._part_rep[a:b], rows).astype(np.int32) if self._multi else None
         return SiteBatch(feats=feats, read_off=read_off, kmer_idx=kmer_idx, read_ids=read_ids,
                          tx_ids=self._tx_bytes[lo:hi].astype(str),
-                         tx_pos=self._pos[lo:hi], kmers=centre, read_rep=rep)
+                         tx_pos=self._pos[lo:hi], kmers=centre, read_rep=rep, tx_bytes=self._tx_bytes[lo:hi])
 
     def close(self):
         for fd in self._files.values():

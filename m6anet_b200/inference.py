@@ -76,7 +76,7 @@ def _tx_buffer(batch: SiteBatch):
     cached = getattr(batch, "_tx_buffer", None)
     if cached is not None:
         return cached
-    ids = np.asarray(batch.tx_ids)
+    ids = np.asarray(batch.tx_ids if batch.tx_bytes is None else batch.tx_bytes)
     if ids.dtype.kind != "S":
         ids = np.char.encode(ids.astype(str), "utf-8") if len(ids) else np.zeros(0, dtype="S1")
     width = max(ids.dtype.itemsize, 1)

@@ -491,3 +491,27 @@ def test_ingest_fuzz_accepts_only_what_json_accepts():
     spec.loader.exec_module(mod)
     stats = mod.run(250, seed=3, verbose=False)
     assert stats["ok"] + stats["rejected"] == 250 and stats["rejected"] > 100 and stats["ok"] > 0
+
+
+def test_csv_writers_on_ingested_batches_equal_python_formatting(bundled_dir):
+    """The path run_inference takes: load_sites() batches (transcript ids as fixed-width bytes) -> native writers."""
+    import tempfile
+    from m6anet_b200 import constants as C
+    from m6anet_b200.data import NanopolishDS
+    from m6anet_b200.inference import write_indiv_rows, write_site_rows
+    ds = NanopolishDS(bundled_dir, 20, C.DEFAULT_NORM_PATH)
+    b = ds.load_sites(3, 60, n_threads=2)
+    assert b.tx_bytes is not None and b.tx_bytes.dtype.kind == "S" and list(b.tx_bytes.astype(str)) == list(b.tx_ids)
+    rng = np.random.default_rng(0)
+    n = np.diff(b.read_off)
+    rp, sp = rng.random(int(n.sum())).astype(np.float32), rng.random(b.n_sites).astype(np.float32)
+    mc = np.minimum(rng.integers(0, 700, b.n_sites), n).astype(np.int32)
+    with tempfile.TemporaryFile() as f, tempfile.TemporaryFile() as g:
+        write_site_rows(f, b, sp, mc, 3)
+        write_indiv_rows(g, b, rp, 3)
+        f.seek(0), g.seek(0)
+        fl, gl = f.read().decode(), g.read().decode()
+    assert fl == "".join('%s,%d,%s,%.16f,%s,%.16f\n' % (t, p, k, float(a), km, m / k) for t, p, k, a, km, m in
+                         zip(b.tx_ids, b.tx_pos, n, sp, b.kmers, mc.astype(np.float64)))
+    assert gl == "".join('%s,%d,%s,%.16f\n' % (t, p, r, float(a)) for t, p, r, a in
+                         zip(np.repeat(b.tx_ids, n), np.repeat(b.tx_pos, n), b.read_ids, rp))
