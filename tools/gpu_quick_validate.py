@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Torch-free GPU check of the validate()-style entry points against the oracle (seconds, not minutes: no torch import).
-    python tools/gpu_quick_validate.py [out.json]
+    python tools/gpu_quick_validate.py [out.json] [--time]
 Runs m6a_mil_validate_host_f32 (Floyd bags / inference stream, prod|mean|max, bag sizes 20 and 7) on the 288 synthetic
 golden sites and m6a_mil_validate_f32 with explicit bags (the reference's replayed MT19937 draws) on the bundled sets,
 device memory through libcudart + ctypes.  Prints max abs differences; exits non-zero above 2e-6."""
@@ -96,11 +96,28 @@ for pool in ("prod", "mean", "max"):
         note(f"device explicit bags {pool} {mode} vs reference validate()", (bag.T, vg[f"{pool}_{mode}_y_pred"]))
         for p in d:
             rt.cudaFree(p)
+# ---- timing (optional: `--time`): validate()-style passes next to the inference pass on the same synthetic sites -------
+if "--time" in sys.argv:
+    rng = np.random.default_rng(0)
+    S, n = 200_000, 50
+    tf = rng.standard_normal((S * n, 9), dtype=np.float32)
+    to = (np.arange(S + 1, dtype=np.int64) * n)
+    tk = kmer[rng.integers(0, len(kmer), S)]
+    timing = {}
+    for name, fn in (("validate_host 5 passes, bags of 20 without replacement", lambda: eng.validate_host(tf, to, tk, 5, seed=1)),
+                     ("validate_host 1000 passes", lambda: eng.validate_host(tf, to, tk, 1000, seed=1)),
+                     ("infer_host 1000 iterations", lambda: eng.infer_host(tf, to, tk, 1000, seed=1))):
+        fn()
+        best = min((lambda t: (fn(), time.perf_counter() - t)[1])(time.perf_counter()) for _ in range(3))
+        timing[name] = {"ms": best * 1e3, "sites_per_s": S / best}
+        print(f"{name:60s} {best * 1e3:8.1f} ms  {S / best / 1e6:7.2f} M sites/s (host buffers, {S} sites x {n} reads)", flush=True)
+    res["timing"] = timing
 res["seconds"] = time.time() - t0
 res["ok"] = res["worst"] <= 2e-6
-if len(sys.argv) > 1:
-    os.makedirs(os.path.dirname(os.path.abspath(sys.argv[1])), exist_ok=True)
-    with open(sys.argv[1], "w") as fh:
+out_path = next((x for x in sys.argv[1:] if not x.startswith("--")), None)
+if out_path:
+    os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
+    with open(out_path, "w") as fh:
         json.dump(res, fh, indent=1)
 print("OK" if res["ok"] else "FAIL", f"worst {res['worst']:.3e} in {res['seconds']:.1f} s")
 sys.exit(0 if res["ok"] else 1)
