@@ -311,6 +311,21 @@ def main():
                 "traffic": traffic, "kernel": "mil_infer_kernel", "kernel_ms": k_avg_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "the kernel is fp32-issue bound (>=6.2k FMA per read + 20k samples per site); see DESIGN.md"}
+    # algorithmic FLOP per site (reference formulation, 7 082 MAC per read) and samples per site, and what the
+    # encoder alone achieves against the FP32 FMA peak of the device (n_SMs x 128 lanes x 2 FLOP x SM clock) -- the pipe
+    # that actually bounds this kernel.  The Monte-Carlo draws (integer multiplies on the same pipe) are not counted.
+    try:
+        n_reads_rank = int(feats_h.shape[0])
+        props = torch.cuda.get_device_properties(dev)
+        sm_mhz = float(getattr(props, "clock_rate", 1965000)) / 1e3
+        fp32_peak = props.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+        fp32_achieved = n_reads_rank * 14164.0 / (k_avg_ms * 1e-3) / 1e12
+        roofline["compute"] = {"flop_per_site": 14164.0 * n_reads_rank / max(ns, 1), "samples_per_site": 20 * a.iters,
+                               "achieved_tflops_fp32": fp32_achieved, "peak_tflops_fp32": fp32_peak,
+                               "frac": fp32_achieved / fp32_peak if fp32_peak > 0 else None,
+                               "peak_source": f"{props.multi_processor_count} SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz (nominal)"}
+    except Exception as exc:      # informative only: never fail the bench line over it
+        roofline["compute"] = {"error": repr(exc)}
 
     # ---- e2e: host buffers through the C-ABI host call, H2D + kernel + D2H inside the timed region ------
     e2e = None
