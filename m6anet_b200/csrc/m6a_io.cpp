@@ -216,6 +216,7 @@ bool parse_part(IngestCtx& c, int64_t pi, std::vector<char>& buf) {
         return false;
       }
       if (nv != row_w || row >= p.n_rows) return false;
+      if (!(std::fabs(vals[row_w - 1]) < 9.2e18)) return false;      // read id must fit int64 (NaN / inf / 1e300 do not)
       float* out = c.feats + (p.row_off + row) * n_sig;
       for (int k = 0; k < n_sig; ++k) out[k] = static_cast<float>((vals[col0 + k] - mean[k]) / stdv[k]);
       c.read_ids[p.row_off + row] = static_cast<int64_t>(vals[row_w - 1]);
