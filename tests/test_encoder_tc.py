@@ -123,6 +123,40 @@ def test_packed_image_matches_descriptor_geometry_and_keeps_accuracy(tclib, tag,
     assert np.abs(p - want).max() < 2e-6
 
 
+def _cutlass_include():
+    import importlib.util
+    for pkg, sub in (("flashinfer", "data/cutlass/include"), ("tilelang", "3rdparty/cutlass/include")):
+        spec = importlib.util.find_spec(pkg)
+        if spec and spec.submodule_search_locations:
+            path = os.path.join(list(spec.submodule_search_locations)[0], sub)
+            if os.path.exists(os.path.join(path, "cute", "arch", "mma_sm100_desc.hpp")):
+                return path
+    return None
+
+
+def test_descriptors_equal_cute_encoders(tclib, tmp_path):
+    """The hand-packed instruction descriptors and the LBO / SBO / layout fields of the shared-memory descriptors equal
+    what CuTe's own encoders (vendored CUTLASS headers) produce for the same shapes and operand layout; CuTe also
+    statically asserts that the layout is a canonical UMMA K-major one (tools/cute_desc_check.cu, host run)."""
+    inc = _cutlass_include()
+    if inc is None:
+        pytest.skip("no vendored CUTLASS headers in this environment")
+    exe = tmp_path / "cute_desc_check"
+    res = subprocess.run(["nvcc", "-std=c++17", f"-I{inc}", "-arch=sm_100a", "-o", str(exe),
+                          os.path.join(ROOT, "tools", "cute_desc_check.cu")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout
+    geo = np.zeros(16, dtype=np.int64)
+    assert tclib.m6a_tc_geometry(geo.ctypes.data_as(C.c_void_p)) == 0
+    sbo, lbo1, lbo2, idesc1, idesc2 = int(geo[8]), int(geo[9]), int(geo[11]), int(geo[13]), int(geo[14])
+    idesc = {(int(a), int(b)): int(c) for _, a, b, c in (l.split() for l in out.splitlines() if l.startswith("idesc"))}
+    ops = {int(l.split()[1]): tuple(int(x) for x in l.split()[2:]) for l in out.splitlines() if l.startswith("operand")}
+    assert idesc[(128, 160)] == idesc1 and idesc[(128, 32)] == idesc2
+    assert ops[160] == (lbo1 >> 4, sbo >> 4, 0, 1)          # W1: LBO, SBO in 16-byte units, SWIZZLE_NONE, version 1
+    assert ops[32] == (lbo2 >> 4, sbo >> 4, 0, 1)           # W2
+    assert ops[128] == (128 * 16 >> 4, sbo >> 4, 0, 1)      # X tile
+
+
 WORKER = textwrap.dedent("""
     import ctypes as C, os, sys
     import numpy as np, torch
