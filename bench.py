@@ -354,6 +354,10 @@ def main():
                "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps, "bytes_are": "per rank",
                "timer": "host perf_counter around the synchronous C-ABI call, max over ranks",
                "matches_resident_path": same}
+        # the host-buffer path is bound by PCIe: report the H2D rate it sustains next to the measured pinned-copy rate
+        # (tools/microbench: 55.1 GB/s H2D, 56.7 GB/s D2H on this pool's B200 boxes)
+        e2e["h2d_gbs"] = e2e["h2d_bytes_per_step"] / (dt / e_steps) / 1e9
+        e2e["pcie_h2d_peak_gbs"] = 55.1
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
     cpu = None
