@@ -202,6 +202,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = []
+    if world > 1 and os.environ.get("M6A_NO_NUMA_BIND") != "1":
+        # one process per GPU: stay on the GPU's socket so that pinned staging buffers are first-touched next to it
+        from m6anet_b200.dist import bind_host_to_device
+        numa_cpus = bind_host_to_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner with printf on fd 1 at communicator creation; stdout must carry only the JSON
@@ -382,7 +387,9 @@ def main():
                        "parallelism": f"site-sharded x{n_gpus}" + (", 1 NCCL all-gather/step" if n_gpus > 1 else ""),
                        "l2": f"inputs ({feats_h.nbytes / 1e6:.0f} MB/rank) larger than L2" if feats_h.nbytes > 126e6
                              else "inputs smaller than L2 (not flushed)",
-                       "launch": launch},
+                       "launch": launch,
+                       "host_binding": (f"rank 0 bound to {len(numa_cpus)} GPU-local CPUs (NVML affinity)" if numa_cpus
+                                        else "none")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "per_rank": per_rank,
             "gpu_launches": a.steps * launch["n_launches"],
         }

@@ -19,6 +19,40 @@ def env_world() -> Tuple[int, int, int]:
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def bind_host_to_device(device_index: int, min_cpus: int = 4) -> List[int]:
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device_index` (its NUMA node / PCIe root), so
+    that the pinned staging buffers a rank allocates afterwards are first-touched next to its GPU and its ingest / CSV
+    threads stay on that socket.  One process per GPU on a two-socket 8-GPU box otherwise sends half of the ranks' H2D
+    traffic across the inter-socket link.  Best effort: returns the CPU list it bound to, or [] (nothing changed) when
+    NVML is unavailable, CUDA_VISIBLE_DEVICES remaps devices in a way NVML cannot see, or the set is implausibly small."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if device_index >= len(ids) or not ids[device_index].isdigit():
+                    return []
+                physical = int(ids[device_index])
+            else:
+                physical = device_index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(physical)
+            n_cpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+            cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        finally:
+            pynvml.nvmlShutdown()
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in cpus if c in allowed)
+        if len(cpus) < min_cpus or len(cpus) >= len(allowed):
+            return []
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:      # noqa: BLE001 - purely an optimisation
+        return []
+
+
 def shard_bounds(n_reads: np.ndarray, world_size: int) -> List[int]:
     """Contiguous site ranges with (nearly) equal total reads.  Returns world_size + 1 site indices."""
     n_reads = np.asarray(n_reads, dtype=np.int64)

@@ -165,6 +165,9 @@ def run_inference(model: MILModel, dl, args):
     if world > 1:     # torch only for the multi-GPU plumbing (torch.distributed over NCCL)
         import torch
         import torch.distributed as dist
+        if os.environ.get("M6A_NO_NUMA_BIND") != "1":
+            from .dist import bind_host_to_device
+            bind_host_to_device(dev)      # ingest / CSV threads and pinned staging stay on the GPU's socket (best effort)
         torch.cuda.set_device(dev)
         if not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

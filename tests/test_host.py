@@ -515,3 +515,33 @@ def test_csv_writers_on_ingested_batches_equal_python_formatting(bundled_dir):
                          zip(b.tx_ids, b.tx_pos, n, sp, b.kmers, mc.astype(np.float64)))
     assert gl == "".join('%s,%d,%s,%.16f\n' % (t, p, r, float(a)) for t, p, r, a in
                          zip(np.repeat(b.tx_ids, n), np.repeat(b.tx_pos, n), b.read_ids, rp))
+
+
+def test_bind_host_to_device_is_best_effort(monkeypatch):
+    """No NVML / implausible answers change nothing; a proper GPU-local CPU mask is applied (NVML bit words -> CPU list,
+    CUDA_VISIBLE_DEVICES remapping honoured)."""
+    import sys
+    import types
+    from m6anet_b200 import dist as D
+    before = os.sched_getaffinity(0)
+    monkeypatch.setitem(sys.modules, "pynvml", None)            # import fails
+    assert D.bind_host_to_device(0) == [] and os.sched_getaffinity(0) == before
+    allowed = sorted(before)
+    if len(allowed) < 8:
+        pytest.skip("needs >= 8 CPUs to exercise the binding")
+    local = allowed[: len(allowed) // 2]
+    seen = {}
+    fake = types.SimpleNamespace(
+        nvmlInit=lambda: None, nvmlShutdown=lambda: None,
+        nvmlDeviceGetHandleByIndex=lambda i: seen.setdefault("index", i),
+        nvmlDeviceGetCpuAffinity=lambda h, n: [sum(1 << (c - 64 * w) for c in local if c // 64 == w) for w in range(n)])
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    applied = []
+    monkeypatch.setattr(os, "sched_setaffinity", lambda pid, cpus: applied.append(list(cpus)))
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "3,5")
+    assert D.bind_host_to_device(1) == local and seen["index"] == 5 and applied == [local]
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "GPU-deadbeef")
+    assert D.bind_host_to_device(0) == []                        # UUID form: not resolved, nothing changed
+    fake.nvmlDeviceGetCpuAffinity = lambda h, n: [sum(1 << (c % 64) for c in allowed if c // 64 == w) for w in range(n)]
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES")
+    assert D.bind_host_to_device(0) == []                        # every CPU is local: single socket, nothing to do
