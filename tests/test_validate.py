@@ -442,3 +442,44 @@ def test_validate_end_to_end_on_the_labelled_bundled_data(vgold, bundled_flat, l
 
     res_t = validate(model, ds, "cuda:0", torch_criterion, 5, seed=3)
     assert abs(res_t["avg_loss"] - res["avg_loss"]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_validate_properties_at_scale(synthetic_inputs):
+    """100 000 ragged sites (2.9 M reads), 64 passes: size-independent properties of bags drawn WITHOUT replacement.
+      * mean pooling is an unbiased estimator of the site's mean read probability (each read is in a bag w.p. k/n);
+      * max pooling never exceeds the site maximum and noisy-OR is never below max pooling (1 - prod(1-p) >= max p);
+      * a site with exactly k reads gives the same value in every pass;
+      * the result does not depend on how the sites are cut into shards / chunks."""
+    rng = np.random.default_rng(5)
+    S, k, passes = 100_000, 20, 64
+    n = np.minimum(20 + rng.geometric(0.12, S) - 1, 400)
+    n[::97] = 20
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    feats = rng.standard_normal((int(off[-1]), 9), dtype=np.float32)
+    kmer = synthetic_inputs["kmer_idx"][rng.integers(0, len(synthetic_inputs["kmer_idx"]), S)]
+    eng = engine()
+    rp, bag_mean, _, _ = eng.validate_host(feats, off, kmer, passes, seed=21, pooling="mean")
+    _, bag_max, _, _ = eng.validate_host(feats, off, kmer, passes, seed=21, pooling="max", n_chunks=7)
+    _, bag_prod, site_prod, _ = eng.validate_host(feats, off, kmer, passes, seed=21, pooling="prod", n_chunks=3)
+    assert np.isfinite(bag_mean).all() and np.isfinite(bag_max).all() and np.isfinite(bag_prod).all()
+    p64 = rp.astype(np.float64)
+    site_mean = np.add.reduceat(p64, off[:-1]) / n
+    site_sq = np.add.reduceat(p64 * p64, off[:-1]) / n
+    var_read = np.maximum(site_sq - site_mean ** 2, 0)
+    # variance of the mean of k draws without replacement: var/k * (n-k)/(n-1); over `passes` independent bags
+    sd = np.sqrt(var_read / k * (n - k) / np.maximum(n - 1, 1) / passes)
+    zscore = (bag_mean.astype(np.float64).mean(axis=1) - site_mean) / np.maximum(sd, 1e-9)
+    full = n == k
+    assert np.abs(zscore[~full]).max() < 8 and abs(zscore[~full].mean()) < 0.03          # unbiased, calibrated
+    assert np.abs(bag_mean[full] - site_mean[full, None]).max() < 1e-6                    # the bag is the whole site
+    assert (np.ptp(bag_prod[full], axis=1) == 0).all() and (np.ptp(bag_max[full], axis=1) == 0).all()
+    site_max = np.maximum.reduceat(rp, off[:-1])
+    assert (bag_max <= site_max[:, None]).all() and (bag_max > 0).all()
+    assert (bag_prod >= bag_max - 1e-6).all() and (bag_prod <= 1).all()                   # 1 - prod(1-p) >= max p
+    assert np.abs(site_prod - bag_prod.astype(np.float64).mean(axis=1)).max() < 2e-6
+    # sharding independence at scale: the second half scored alone with its site_id_base
+    h = S // 2
+    _, bag_b, _, _ = eng.validate_host(feats[off[h]:], off[h:] - off[h], kmer[h:], passes, seed=21, pooling="prod",
+                                       site_id_base=h)
+    assert np.array_equal(bag_b, bag_prod[h:])
