@@ -270,6 +270,9 @@ bool write_all(int fd, const char* p, size_t n) {
 struct OutBuf {
   char* p = nullptr;
   size_t len = 0, cap = 0;
+  OutBuf() = default;
+  OutBuf(const OutBuf&) = delete;
+  OutBuf& operator=(const OutBuf&) = delete;
   ~OutBuf() { free(p); }
   bool ensure(size_t extra) {          // room for `extra` more bytes
     if (len + extra <= cap) return true;
