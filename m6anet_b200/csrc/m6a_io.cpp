@@ -83,13 +83,35 @@ inline const char* expect(const char* r, const char* e, char ch) {
   r = skip_ws(r, e);
   return (r < e && *r == ch) ? r + 1 : nullptr;
 }
-// expects a string without escapes; returns the position after the closing quote, [*s0, *s1) = contents
+// expects a string without escapes; returns the position after the closing quote, [*s0, *s1) = contents.
+// Non-ASCII bytes must form valid UTF-8 (json.loads decodes the line as UTF-8 and refuses anything else).
 inline const char* expect_string(const char* r, const char* e, const char** s0, const char** s1) {
   r = expect(r, e, '"');
   if (!r) return nullptr;
   *s0 = r;
-  for (; r < e && *r != '"'; ++r)
-    if (*r == '\\' || static_cast<unsigned char>(*r) < 0x20) return nullptr;   // escapes never occur in ids / k-mers
+  while (r < e && *r != '"') {
+    const unsigned char c = static_cast<unsigned char>(*r);
+    if (c == '\\' || c < 0x20) return nullptr;          // escapes never occur in ids / k-mers
+    if (c < 0x80) {
+      ++r;
+      continue;
+    }
+    int extra;                                            // continuation bytes of the sequence
+    unsigned cp;
+    if (c >= 0xC2 && c <= 0xDF) { extra = 1; cp = c & 0x1Fu; }
+    else if (c >= 0xE0 && c <= 0xEF) { extra = 2; cp = c & 0x0Fu; }
+    else if (c >= 0xF0 && c <= 0xF4) { extra = 3; cp = c & 0x07u; }
+    else return nullptr;
+    if (e - r <= extra) return nullptr;
+    for (int i = 1; i <= extra; ++i) {
+      const unsigned char t = static_cast<unsigned char>(r[i]);
+      if ((t & 0xC0u) != 0x80u) return nullptr;
+      cp = (cp << 6) | (t & 0x3Fu);
+    }
+    if ((extra == 2 && cp < 0x800u) || (extra == 3 && (cp < 0x10000u || cp > 0x10FFFFu))) return nullptr;   // overlong / range
+    // (surrogate code points U+D800..DFFF are let through: json.loads decodes with 'surrogatepass')
+    r += extra + 1;
+  }
   if (r >= e) return nullptr;
   *s1 = r;
   return r + 1;

@@ -470,6 +470,23 @@ def test_native_number_parser_is_correctly_rounded_and_strict(tmp_path):
                    ok.replace('"t"', '"t\\"x"')):       # escapes never occur in transcript ids
         assert ingest(broken)[0] == -6, broken
     assert ingest(ok, n_rows=2)[0] == -6 and ingest(ok, n_rows=0)[0] == -6           # row count must match data.info
+    # transcript ids: any valid UTF-8 without escapes, exactly when json.loads can decode the line
+    pool = [0x41, 0x7A, 0xC2, 0xA9, 0xE2, 0x82, 0xAC, 0xF0, 0x9F, 0x98, 0x80, 0xED, 0xA0, 0x80, 0xC0, 0xAF, 0xFF, 0xE0, 0x9F, 0xF4, 0x90]
+    for _ in range(400):
+        name = bytes(rng.choice(pool, int(rng.integers(1, 6))).tolist())
+        line_b = b'{"' + name + b'":{"1":{"AGGACTG":[' + good_row.encode() + b']}}}\n'
+        try:
+            json.loads(line_b)
+            valid = True
+        except ValueError:
+            valid = False
+        path.write_bytes(line_b)
+        parts = np.zeros(1, dtype=_cabi.PART_DTYPE)
+        parts[0] = (0, 0, 0, len(line_b), 0, 1, 0, 1, 0)
+        f_, i_, k_ = np.zeros((1, 9), np.float32), np.zeros(1, np.int64), np.zeros((1, 3), np.int32)
+        z_, o_ = np.zeros((1024, 3)), np.ones((1024, 3))
+        rc = L.m6a_ingest_parts(paths, 1, vp(parts), 1, 1, vp(z_), vp(o_), vp(kid), vp(f_), vp(i_), vp(k_), 1, None)
+        assert (rc == 0) == valid, (name, rc, valid)
     # byte range past the end of the file: data.info does not belong to this data.json
     path.write_text(ok)
     parts = np.zeros(1, dtype=_cabi.PART_DTYPE)
