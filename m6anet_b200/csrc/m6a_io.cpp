@@ -422,6 +422,7 @@ int load_info(const char* path, InfoFile& f) {
     got += static_cast<size_t>(r);
   }
   close(fd);
+  if (f.text.empty()) return M6A_EPARSE;      // not even a header
   // header
   const char* p = f.text.data();
   const char* e = p + f.text.size();
