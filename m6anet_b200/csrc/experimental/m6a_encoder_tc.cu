@@ -35,179 +35,25 @@
 
 #include "../../../include/m6anet_b200.h"
 #include "m6a_encoder_tc.h"
+#include "m6a_tc_device.cuh"
 
 namespace m6a {
 namespace tc {
 
-struct alignas(128) Smem {
-  float x[kK1 / 4][kTileM][4];       // A of Linear-1 (hi = the value itself)            8 KB
-  float xlo[kK1 / 4][kTileM][4];     //                                                  8 KB
-  float w1[kK1 / 4][kN1][4];         // B of Linear-1: [k-chunk][hidden unit][4]         10 KB
-  float w1lo[kK1 / 4][kN1][4];
-  float w2[kK2 / 4][kN2][4];         // B of Linear-2: [k-chunk][output][4]              20 KB
-  float w2lo[kK2 / 4][kN2][4];
-  float b2[kN2];
-  float w3[kN2];
-  float b3;
-  uint32_t tmem_base;
-  alignas(8) unsigned long long bar_l1;        // Linear-1 accumulators ready
-  alignas(8) unsigned long long bar_stage[2];  // MMAs that read lo-staging buffer b have completed
-  alignas(8) unsigned long long bar_l2;        // Linear-2 accumulators ready
-};
-static_assert(offsetof(Smem, xlo) % 128 == 0 && offsetof(Smem, w1) % 128 == 0 && offsetof(Smem, w2) % 128 == 0 &&
-                  offsetof(Smem, w1lo) % 128 == 0 && offsetof(Smem, w2lo) % 128 == 0,
-              "UMMA operands must start on a 128-byte core-matrix boundary");
+size_t smem_bytes() { return sizeof(TcSmem); }
 
-size_t smem_bytes() { return sizeof(Smem); }
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spins = 0; !done; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (spins > (1u << 26)) __trap();   // a lost arrival must not hang the GPU
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-// generic-proxy writes to shared memory -> visible to the async proxy (the tensor core reads operands through it)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_in_smem, uint32_t cols) {   // one full warp
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_in_smem)), "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_free(uint32_t taddr, uint32_t cols) {            // the same warp
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// MMA completion -> one arrival on an mbarrier (implies tcgen05.fence::before_thread_sync)
-__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, cute/arch/mma_sm100_desc.hpp):
-//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (between the two 16-byte k-chunks of one K-step),
-//   [32,46) stride byte offset >> 4 (between 8-row core matrices), [46,48) version = 1, [61,64) layout = 0 (SWIZZLE_NONE)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;
-  return d;
-}
-// Instruction descriptor, kind::tf32, D = float32 (cute::UMMA::InstrDescriptor): [4,6) c_format = 1 (F32),
-// [7,10) a_format = 2 (TF32), [10,13) b_format = 2, [15] a_major = 0 (K), [16] b_major = 0 (K), [17,23) N >> 3, [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
-}
-
-// D[tmem] (+)= A[smem] . B[smem]
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      :
-      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem]
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      :
-      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-
-// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base lane + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
-      :
-      : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
-        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
-        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]), "r"(taddr)
-      : "memory");
-}
-
-__device__ __forceinline__ float trunc_tf32(float f) { return __uint_as_float(__float_as_uint(f) & 0xFFFFE000u); }
-
-// ---- the kernel ------------------------------------------------------------------------------------------------------------
+// ---- the stand-alone encoder kernel: 128 threads, one tile of 128 consecutive reads at a time ---------------------------------
 __global__ void __launch_bounds__(kThreads, 2)
 read_encoder_tc_kernel(const EncoderArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-
-  // ---- one-time: weights -> shared memory (already in the UMMA byte layout), mbarriers, TMEM ----------------------------
-  {
-    const float4* src = reinterpret_cast<const float4*>(a.image);
-    float4* dst = reinterpret_cast<float4*>(sm.w1);
-    constexpr int n4 = (2 * kK1 * kN1 + 2 * kK2 * kN2) / 4;      // w1, w1lo, w2, w2lo are contiguous in both
-    for (int i = tid; i < n4; i += kThreads) dst[i] = __ldg(src + i);
-    if (tid < kN2) {
-      sm.b2[tid] = a.image->b2[tid];
-      sm.w3[tid] = a.image->w3[tid];
-    }
-    if (tid == 0) {
-      sm.b3 = a.image->b3;
-      mbar_init(&sm.bar_l1, 1);
-      mbar_init(&sm.bar_stage[0], 1);
-      mbar_init(&sm.bar_stage[1], 1);
-      mbar_init(&sm.bar_l2, 1);
-      fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(&sm.tmem_base, kTmemCols);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-  }
-  const uint32_t tmem = sm.tmem_base;                                   // lane 0, first allocated column
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;   // this warp's TMEM lane quadrant
-  const uint32_t d1 = tmem + kColD1, lo_stage = tmem + kColLo, d2 = tmem + kColD2;
-  constexpr uint32_t idesc1 = make_idesc(kTileM, kN1), idesc2 = make_idesc(kTileM, kN2);
-  const uint32_t sx = smem_u32(sm.x), sxlo = smem_u32(sm.xlo), sw1 = smem_u32(sm.w1), sw1lo = smem_u32(sm.w1lo);
-  const uint32_t sw2 = smem_u32(sm.w2), sw2lo = smem_u32(sm.w2lo);
-  uint32_t ph_l1 = 0, ph_l2 = 0, ph_stage[2] = {0, 0};
+  TcState st;
+  tc_setup(sm, st, a.image, tid, kThreads);
 
   const long long n_tiles = (a.total_reads + kTileM - 1) / kTileM;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // ---- stage: [x(9) | emb(6) | 1] of read r -> x, x_lo (UMMA K-major layout, one 16-byte k-chunk per store) ----------
+    // ---- stage: [x(9) | emb(6) | 1] of read r ----------------------------------------------------------------------------
     const long long r = tile * kTileM + tid;
     const bool valid = r < a.total_reads;
     float in[kK1];
@@ -236,100 +82,11 @@ read_encoder_tc_kernel(const EncoderArgs a) {
       }
       in[kK1 - 1] = 1.0f;                                 // bias column
     }
-#pragma unroll
-    for (int j = 0; j < kK1 / 4; ++j) {
-      float4 h = make_float4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]);
-      float4 l = make_float4(h.x - trunc_tf32(h.x), h.y - trunc_tf32(h.y), h.z - trunc_tf32(h.z), h.w - trunc_tf32(h.w));
-      *reinterpret_cast<float4*>(sm.x[j][tid]) = h;
-      *reinterpret_cast<float4*>(sm.xlo[j][tid]) = l;
-    }
-    fence_proxy_async();
-    tc_fence_before();       // the previous tile's tcgen05.ld of D1 / D2 are ordered before the MMAs that overwrite them
-    __syncthreads();
-
-    // ---- Linear-1: D1[128 x 160] = X . W1^T as 3 TF32 products per K-step -----------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < kK1 / 8; ++ks) {
-        const uint64_t ax = make_desc(sx + ks * kStepX, kLboX, kSbo);
-        const uint64_t axlo = make_desc(sxlo + ks * kStepX, kLboX, kSbo);
-        const uint64_t bw = make_desc(sw1 + ks * kStepW1, kLboW1, kSbo);
-        const uint64_t bwlo = make_desc(sw1lo + ks * kStepW1, kLboW1, kSbo);
-        mma_ss(d1, ax, bw, idesc1, ks > 0 ? 1u : 0u);
-        mma_ss(d1, axlo, bw, idesc1, 1u);
-        mma_ss(d1, ax, bwlo, idesc1, 1u);
-      }
-      tc_commit(&sm.bar_l1);
-    }
-    mbar_wait(&sm.bar_l1, ph_l1);
-    ph_l1 ^= 1u;
-    tc_fence_after();
-
-    // ---- relu + split per chunk of 32 hidden units, Linear-2 on the chunk -----------------------------------------------
-#pragma unroll 1
-    for (int c = 0; c < kN1 / kChunk; ++c) {
-      const int b = c & 1;
-      uint32_t v[32], l[32];
-      tmem_ld32(d1 + lane_base + c * kChunk, v);
-      tc_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float h = fmaxf(__uint_as_float(v[i]), 0.0f);
-        v[i] = __float_as_uint(h);
-        l[i] = __float_as_uint(h - trunc_tf32(h));
-      }
-      if (c >= 2) {            // the MMAs of chunk c-2 have finished reading staging buffer b
-        mbar_wait(&sm.bar_stage[b], ph_stage[b]);
-        ph_stage[b] ^= 1u;
-        tc_fence_after();
-      }
-      tmem_st32(d1 + lane_base + c * kChunk, v);                    // A_hi of Linear-2, in place
-      tmem_st32(lo_stage + lane_base + b * kChunk, l);              // A_lo
-      tc_wait_st();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < kChunk / 8; ++ks) {
-          const int kstep = c * (kChunk / 8) + ks;
-          const uint64_t bw = make_desc(sw2 + kstep * kStepW2, kLboW2, kSbo);
-          const uint64_t bwlo = make_desc(sw2lo + kstep * kStepW2, kLboW2, kSbo);
-          const uint32_t a_hi = d1 + kstep * 8, a_lo = lo_stage + b * kChunk + ks * 8;
-          mma_ts(d2, a_hi, bw, idesc2, kstep > 0 ? 1u : 0u);
-          mma_ts(d2, a_lo, bw, idesc2, 1u);
-          mma_ts(d2, a_hi, bwlo, idesc2, 1u);
-        }
-        tc_commit(&sm.bar_stage[b]);
-        if (c == kN1 / kChunk - 1) tc_commit(&sm.bar_l2);
-      }
-    }
-    // every commit is consumed exactly once, in order: chunks 3 (buffer 1) and 4 (buffer 0) are still outstanding
-    mbar_wait(&sm.bar_stage[1], ph_stage[1]);
-    ph_stage[1] ^= 1u;
-    mbar_wait(&sm.bar_stage[0], ph_stage[0]);
-    ph_stage[0] ^= 1u;
-    mbar_wait(&sm.bar_l2, ph_l2);
-    ph_l2 ^= 1u;
-    tc_fence_after();
-
-    // ---- epilogue: p = sigmoid(w3 . relu(D2 + b2) + b3) --------------------------------------------------------------------
-    {
-      uint32_t v[32];
-      tmem_ld32(d2 + lane_base, v);
-      tc_wait_ld();
-      float z = sm.b3;
-#pragma unroll
-      for (int k = 0; k < kN2; ++k) z = fmaf(sm.w3[k], fmaxf(__uint_as_float(v[k]) + sm.b2[k], 0.0f), z);
-      const float p = 1.0f / (1.0f + expf(-z));
-      if (valid) a.read_prob[r] = p;
-    }
+    tc_stage_row(sm, tid, in);
+    const float p = tc_encode_tile<1>(sm, st, tid);
+    if (valid) a.read_prob[r] = p;
   }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_free(tmem, kTmemCols);
+  tc_teardown(sm, st, tid);
 }
 
 cudaError_t launch_read_encoder_tc(const EncoderArgs& a, int n_sms, cudaStream_t stream) {
@@ -338,7 +95,7 @@ cudaError_t launch_read_encoder_tc(const EncoderArgs& a, int n_sms, cudaStream_t
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  const int smem = static_cast<int>(sizeof(Smem));
+  const int smem = static_cast<int>(sizeof(TcSmem));
   if (!attr_done[dev]) {
     e = cudaFuncSetAttribute(read_encoder_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -395,11 +152,6 @@ bool pack_image(const float* emb, const float* w1, const float* b1, const float*
 }  // namespace m6a
 
 // ---- C entry points of the experimental library (plain C types; status codes of include/m6anet_b200.h) -----------------
-struct m6a_tc_encoder {
-  void* d_image;
-  int n_kmer, emb_dim, n_sms;
-};
-
 // weights as for m6a_model_create (HOST pointers, BatchNorm folded into w1/b1); uploads the packed image to the current device
 extern "C" int m6a_tc_create(const m6a_weights_t* w, m6a_tc_encoder** out) {
   if (!w || !out) return M6A_EINVAL;

@@ -6,6 +6,12 @@
 
 #include "../m6a_layout.h"
 
+// handle of the experimental library's C entry points (m6a_tc_create / m6a_tc_read_probs_f32 / m6a_tc_mil_infer_f32)
+struct m6a_tc_encoder {
+  void* d_image;     // WeightImageTc on the device
+  int n_kmer, emb_dim, n_sms;
+};
+
 namespace m6a {
 namespace tc {
 
@@ -30,6 +36,15 @@ constexpr uint32_t kLboW2 = kN2 * 16;
 constexpr uint32_t kStepX = 2 * kLboX;            // one K-step (8 tf32 = 2 k-chunks)
 constexpr uint32_t kStepW1 = 2 * kLboW1;
 constexpr uint32_t kStepW2 = 2 * kLboW2;
+
+// Instruction descriptor, kind::tf32, D = float32 (cute::UMMA::InstrDescriptor): [4,6) c_format = 1 (F32),
+// [7,10) a_format = 2 (TF32), [10,13) b_format = 2, [15] a_major = 0 (K), [16] b_major = 0 (K), [17,23) N >> 3, [24,29) M >> 4
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
 
 // Weights as the kernel's shared memory holds them (K-major no-swizzle UMMA operands: [k-chunk of 4][row][4]);
 // *lo = w - trunc_tf32(w).  w1 rows = hidden units (BatchNorm folded), columns = [9 signal | 3 x emb | 0.. | b1 at 15].

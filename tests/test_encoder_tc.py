@@ -61,11 +61,15 @@ def read_operand(img_f32, base_bytes, rows, k_total, lbo, sbo, kstep):
 
 
 def test_library_exports(tclib):
-    for sym in ("m6a_tc_create", "m6a_tc_destroy", "m6a_tc_read_probs_f32", "m6a_tc_debug_image", "m6a_tc_geometry"):
+    for sym in ("m6a_tc_create", "m6a_tc_destroy", "m6a_tc_read_probs_f32", "m6a_tc_mil_infer_f32", "m6a_tc_debug_image",
+                "m6a_tc_geometry"):
         getattr(tclib, sym)
     assert tclib.m6a_tc_read_probs_f32(None, None, None, None, 0, 0, None, None) == -1        # M6A_EINVAL
     sass = subprocess.run(["cuobjdump", "-sass", EXP_LIB], capture_output=True, text=True).stdout
-    assert sass.count("UTCHMMA") == 18 and "LDTM" in sass and "STTM" in sass and "UTCBAR" in sass   # 6 + 12 tcgen05.mma
+    # 6 + 12 tcgen05.mma per kernel: the stand-alone encoder and the two instantiations of the fused kernel
+    assert sass.count("UTCHMMA") == 3 * 18 and "LDTM" in sass and "STTM" in sass and "UTCBAR" in sass
+    assert tclib.m6a_tc_mil_infer_f32(None, None, None, None, 0, 0, 0, 20, 10, 0, C.c_float(0.5), None, None, None, None, 0,
+                                      None) == -1
 
 
 @pytest.mark.parametrize("tag", ["HCT116_RNA002", "HEK293T_RNA004", "signal_only"])
@@ -192,7 +196,25 @@ WORKER = textwrap.dedent("""
             worst = max(worst, d)
         L.m6a_tc_destroy(h)
     print("WORST %.3e" % worst)
-    sys.exit(0 if worst <= 5e-6 else 1)
+    # the fused kernel: tensor-core encoder + the product's Monte-Carlo phase, against the oracle on the device stream
+    from oracle import mil_inference
+    st, keep, emb, w = folded("HCT116_RNA002")
+    h = C.c_void_p(); assert L.m6a_tc_create(C.byref(st), C.byref(h)) == 0
+    S, R = len(off) - 1, len(feats)
+    f = torch.from_numpy(feats).to(dev); o = torch.from_numpy(off).to(dev); k = torch.from_numpy(kmer).to(dev)
+    rp = torch.empty(R, device=dev); sp = torch.empty(S, device=dev); mc = torch.empty(S, dtype=torch.int32, device=dev)
+    ws = torch.empty(R // 64 + 2, dtype=torch.int64, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    rc = L.m6a_tc_mil_infer_f32(h, vp(f), vp(o), vp(k), C.c_int64(S), C.c_int64(R), C.c_int64(7_000_000_000), 20, 200,
+                                C.c_uint64(1234), C.c_float(0.033379376), vp(rp), vp(sp), vp(mc), vp(ws),
+                                C.c_int64(ws.numel() * 8), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    orp, osp, omc = mil_inference(oracle_params("HCT116_RNA002"), feats, off, kmer, n_iters=200, seed=1234,
+                                  site_id_base=7_000_000_000)
+    d_read = float(np.abs(rp.cpu().numpy() - orp).max()); d_site = float(np.abs(sp.cpu().numpy() - osp).max())
+    print("fused: max|dp_read| = %.3e  max|dp_site| = %.3e" % (d_read, d_site))
+    sys.exit(0 if worst <= 5e-6 and d_read <= 5e-6 and d_site <= 1e-4 else 1)
 """)
 
 
