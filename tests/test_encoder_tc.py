@@ -18,7 +18,7 @@ import textwrap
 import numpy as np
 import pytest
 
-from conftest import ALL_TAGS, ROOT, load_golden, oracle_params
+from conftest import ROOT, oracle_params
 
 EXP_DIR = os.path.join(ROOT, "m6anet_b200", "csrc", "experimental")
 EXP_LIB = os.path.join(EXP_DIR, "libm6a_encoder_tc.so")
