@@ -10,6 +10,10 @@
  *   oracle_sample_indices the shared index stream (oracle/philox.py: Philox4x32-10-seeded MWC64X lane streams)
  *   oracle_site_probs     _calculate_site_proba on that stream: (1 - prod(1 - p[idx], axis=1)).mean()
  *                         (utils/inference_utils.py:85-86), float32 products, mod_count (:53)
+ *   oracle_sample_bags    bags WITHOUT replacement (oracle/philox.py "Floyd bags"), the device twin of
+ *                         np.random.choice(n, min_reads, replace=False) (utils/data_utils.py:213-214)
+ *   oracle_bag_probs      the evaluation loop of validate() (utils/training_utils.py:236-256): per pass one bag per site,
+ *                         pooled like the model's pooling block (model_blocks/pooling_blocks.py:96-98,127-129,158-160)
  */
 #include <math.h>
 #include <stdint.h>
@@ -118,4 +122,66 @@ void oracle_site_probs(const float *read_prob, const int64_t *read_off, int64_t 
     }
     free(idx);
   }
+}
+
+/* Floyd bags of one site: out [n_iters, n_samples] int32, distinct inside a bag; requires n_reads >= n_samples. */
+void oracle_sample_bags(uint64_t seed, uint64_t site_id, uint32_t n_reads, int n_iters, int n_samples, int32_t *out) {
+  int ipl, n_blocks;
+  block_layout(n_iters, &ipl, &n_blocks);
+  for (int b = 0; b < n_blocks; ++b)
+    for (int l = 0; l < 32; ++l) {
+      uint32_t c[4] = {(uint32_t)l, (uint32_t)b, (uint32_t)site_id, (uint32_t)(site_id >> 32)};
+      philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      uint32_t x = c[0], cy = (uint32_t)(((uint64_t)c[1] * (MWC_A - 1u)) >> 32);
+      if (x == 0 && cy == 0) x = 1;
+      for (int k = 0; k < ipl; ++k) {
+        const long long it = ((long long)b * ipl + k) * 32 + l;
+        if (it >= n_iters) break;
+        int32_t *pick = out + it * n_samples;
+        for (int d = 0; d < n_samples; ++d) {
+          const uint32_t word = x ^ cy;
+          const uint64_t t = (uint64_t)MWC_A * x + cy;
+          x = (uint32_t)t; cy = (uint32_t)(t >> 32);
+          const uint32_t j = n_reads - (uint32_t)n_samples + (uint32_t)d;
+          const uint32_t cand = (uint32_t)(((uint64_t)word * (j + 1u)) >> 32);     /* uniform on [0, j] */
+          int dup = 0;
+          for (int e = 0; e < d; ++e) dup |= (pick[e] == (int32_t)cand);
+          pick[d] = (int32_t)(dup ? j : cand);
+        }
+      }
+    }
+}
+
+/* bag_prob [n_sites, n_iters] float32 (NaN for a site with fewer reads than the bag); pool: 0 noisy-OR, 1 mean, 2 max. */
+void oracle_bag_probs(const float *read_prob, const int64_t *read_off, int64_t s_lo, int64_t s_hi, int64_t site_id_base,
+                      int n_iters, int n_samples, uint64_t seed, int pool, float *bag_prob) {
+  int32_t *idx = (int32_t *)malloc((size_t)n_iters * n_samples * sizeof(int32_t));
+  for (int64_t s = s_lo; s < s_hi; ++s) {
+    const float *p = read_prob + read_off[s];
+    const int64_t n = read_off[s + 1] - read_off[s];
+    float *out = bag_prob + s * n_iters;
+    if (n < n_samples) {
+      for (int it = 0; it < n_iters; ++it) out[it] = NAN;
+      continue;
+    }
+    oracle_sample_bags(seed, (uint64_t)(site_id_base + s), (uint32_t)n, n_iters, n_samples, idx);
+    for (int it = 0; it < n_iters; ++it) {
+      const int32_t *b = idx + it * n_samples;
+      float y;
+      if (pool == 0) {
+        float prod = 1.0f;
+        for (int k = 0; k < n_samples; ++k) prod *= 1.0f - p[b[k]];
+        y = 1.0f - prod;
+      } else if (pool == 1) {
+        float sum = 0.0f;
+        for (int k = 0; k < n_samples; ++k) sum += p[b[k]];
+        y = sum / (float)n_samples;
+      } else {
+        y = p[b[0]];
+        for (int k = 1; k < n_samples; ++k) y = p[b[k]] > y ? p[b[k]] : y;
+      }
+      out[it] = y;
+    }
+  }
+  free(idx);
 }

@@ -160,6 +160,21 @@ def test_oracle_validate_on_device_stream_is_consistent(synthetic_inputs):
     assert abs(full - (1 - np.prod(1 - rp[:20].astype(np.float64)))) < 1e-6
 
 
+def test_c_oracle_validate_equals_numpy_oracle(synthetic_inputs):
+    """oracle/c (used to check EVERY site of full-size jobs) against the NumPy restatement: bags bit-exact, pooled values
+    to float32 rounding of the read encoder."""
+    from oracle import bag_indices, c_oracle, mil_validate
+    si = synthetic_inputs
+    feats, off, kmer = si["feats"], si["read_off"], si["kmer_idx"]
+    P = oracle_params("HCT116_RNA002")
+    for seed, site, n, it, k in ((3, 7, 57, 300, 20), (2**63 + 1, 2**40 + 5, 700, 70, 20), (1, 2, 64, 33, 64), (9, 9, 21, 9, 7)):
+        assert np.array_equal(c_oracle.sample_bags(seed, site, n, it, k), bag_indices(seed, site, n, it, k))
+    for pool in POOLS:
+        rp, bag, _, _ = mil_validate(P, feats, off, kmer, 12, seed=5, site_id_base=2**33, pool=pool)
+        crp, cbag = c_oracle.mil_validate(P, feats, off, kmer, 12, seed=5, site_id_base=2**33, pool=pool)
+        assert np.abs(rp - crp).max() <= 1e-6 and np.abs(bag - cbag).max() <= 1e-6
+
+
 def test_metrics_match_sklearn():
     from sklearn.metrics import auc, precision_recall_curve, roc_curve
     from m6anet_b200.validation import get_accuracy, get_pr_auc, get_roc_auc
@@ -483,3 +498,22 @@ def test_validate_properties_at_scale(synthetic_inputs):
     _, bag_b, _, _ = eng.validate_host(feats[off[h]:], off[h:] - off[h], kmer[h:], passes, seed=21, pooling="prod",
                                        site_id_base=h)
     assert np.array_equal(bag_b, bag_prod[h:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pool", POOLS)
+def test_validate_every_site_of_a_large_job_against_the_c_oracle(synthetic_inputs, pool):
+    """100 000 ragged sites (about 4 M reads), 5 passes: every per-read probability and every bag of every site against
+    the C restatement (oracle/c) on the same device bag stream."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(8)
+    S = 100_000
+    n = rng.integers(20, 61, S)
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    feats = rng.standard_normal((int(off[-1]), 9), dtype=np.float32)
+    kmer = synthetic_inputs["kmer_idx"][rng.integers(0, len(synthetic_inputs["kmer_idx"]), S)]
+    rp, bag, _, _ = engine().validate_host(feats, off, kmer, 5, seed=77, site_id_base=3_000_000_000, pooling=pool)
+    crp, cbag = c_oracle.mil_validate(oracle_params("HCT116_RNA002"), feats, off, kmer, 5, seed=77, site_id_base=3_000_000_000,
+                                      pool=pool)
+    assert np.abs(rp - crp).max() <= 3e-6          # float32 evaluations of 4 M reads sit up to ~2e-6 apart (DESIGN.md section 2)
+    assert np.abs(bag - cbag).max() <= 3e-6
