@@ -11,8 +11,9 @@
 // utils/inference_utils.py:35-37, model_blocks/blocks.py:126,204-205,65,249-255, pooling_blocks.py:52 -- with both Linear
 // blocks on the tensor cores as error-compensated TF32 products (tools/tf32x3_feasibility.py: max |p - p_float64| = 5.9e-7
 // with hardware truncation, 1xTF32 would be 9e-4):
-//      A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo,   A_hi = the float32 value (the tensor core reads its top 19 bits),
-//                                                 A_lo = A - trunc_tf32(A)  (exact in float32)
+//      A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo,   A_hi = trunc_tf32(A) (stored with the low 13 mantissa bits cleared, so the
+//                                                 split is exact whether the hardware truncates or rounds its operands),
+//                                                 A_lo = A - A_hi  (exact in float32)
 //
 // One CTA = 128 threads = one tile of 128 reads (TMEM lanes) at a time, persistent over tiles; 2 CTAs per SM (256 TMEM
 // columns each):
@@ -129,15 +130,17 @@ bool pack_image(const float* emb, const float* w1, const float* b1, const float*
       float w = 0.0f;
       if (k < in1) w = w1[static_cast<size_t>(j) * in1 + k];
       else if (k == kK1 - 1) w = b1[j];
-      img->w1[k / 4][j][k % 4] = w;
-      img->w1lo[k / 4][j][k % 4] = w - trunc_tf32_host(w);
+      const float hi = trunc_tf32_host(w);                      // operands are stored TF32-exact: the split does not
+      img->w1[k / 4][j][k % 4] = hi;                            // depend on how the tensor core converts 32-bit inputs
+      img->w1lo[k / 4][j][k % 4] = trunc_tf32_host(w - hi);
     }
   }
   for (int n = 0; n < kN2; ++n)
     for (int k = 0; k < h1; ++k) {
       const float w = w2[static_cast<size_t>(n) * h1 + k];
-      img->w2[k / 4][n][k % 4] = w;
-      img->w2lo[k / 4][n][k % 4] = w - trunc_tf32_host(w);
+      const float hi = trunc_tf32_host(w);
+      img->w2[k / 4][n][k % 4] = hi;
+      img->w2lo[k / 4][n][k % 4] = trunc_tf32_host(w - hi);
     }
   for (int k = 0; k < kN2; ++k) {
     img->b2[k] = b2[k];

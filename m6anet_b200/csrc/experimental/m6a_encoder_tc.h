@@ -47,7 +47,7 @@ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 // Weights as the kernel's shared memory holds them (K-major no-swizzle UMMA operands: [k-chunk of 4][row][4]);
-// *lo = w - trunc_tf32(w).  w1 rows = hidden units (BatchNorm folded), columns = [9 signal | 3 x emb | 0.. | b1 at 15].
+// w* = trunc_tf32(w), w*lo = trunc_tf32(w - trunc_tf32(w)).  w1 rows = hidden units (BatchNorm folded), columns = [9 signal | 3 x emb | 0.. | b1 at 15].
 struct alignas(16) WeightImageTc {
   float w1[kK1 / 4][kN1][4];
   float w1lo[kK1 / 4][kN1][4];

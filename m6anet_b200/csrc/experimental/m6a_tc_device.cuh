@@ -3,7 +3,7 @@
 //
 // A CTA of W * 128 threads (W = 1 or 2 warps per TMEM lane quadrant) encodes one tile of 128 reads at a time:
 //   tc_setup        weights -> shared memory (UMMA byte layout), mbarriers, 256 TMEM columns
-//   tc_stage_row    thread t < 128 writes the 16 inputs of read t ([x(9) | emb(6) | 1]) and their TF32 residuals as the A
+//   tc_stage_row    thread t < 128 writes the 16 inputs of read t ([x(9) | emb(6) | 1]), truncated to TF32, and their residuals as the A
 //                   operand of Linear-1
 //   tc_encode_tile  Linear-1 (2 K-steps x 3 MMAs, SS) -> per chunk of 32 hidden units: relu, residual, back to TMEM,
 //                   Linear-2 (4 K-steps x 3 MMAs, A from TMEM) -> p = sigmoid(w3 . relu(D2 + b2) + b3) for row t < 128
@@ -209,8 +209,11 @@ __device__ __forceinline__ void tc_teardown(TcSmem& sm, const TcState& st, int t
 __device__ __forceinline__ void tc_stage_row(TcSmem& sm, int row, const float (&in)[kK1]) {
 #pragma unroll
   for (int j = 0; j < kK1 / 4; ++j) {
-    const float4 h = make_float4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]);
-    const float4 l = make_float4(h.x - trunc_tf32(h.x), h.y - trunc_tf32(h.y), h.z - trunc_tf32(h.z), h.w - trunc_tf32(h.w));
+    // hi is stored already truncated to TF32 (low 13 mantissa bits zero), so the split is exact whether the tensor core
+    // truncates or rounds its 32-bit operands; lo = x - hi is exact in float32
+    const float4 f = make_float4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]);
+    const float4 h = make_float4(trunc_tf32(f.x), trunc_tf32(f.y), trunc_tf32(f.z), trunc_tf32(f.w));
+    const float4 l = make_float4(f.x - h.x, f.y - h.y, f.z - h.z, f.w - h.w);
     *reinterpret_cast<float4*>(sm.x[j][row]) = h;
     *reinterpret_cast<float4*>(sm.xlo[j][row]) = l;
   }
@@ -262,8 +265,9 @@ __device__ __forceinline__ float tc_encode_tile(TcSmem& sm, TcState& st, int tid
 #pragma unroll
     for (int i = 0; i < kShare; ++i) {
       const float h = fmaxf(__uint_as_float(v[i]), 0.0f);
-      v[i] = __float_as_uint(h);
-      l[i] = __float_as_uint(h - trunc_tf32(h));
+      const float hi = trunc_tf32(h);          // stored truncated: exact split under either operand-conversion behaviour
+      v[i] = __float_as_uint(hi);
+      l[i] = __float_as_uint(h - hi);
     }
     if (c >= 2) {            // the MMAs of chunk c-2 have finished reading staging buffer b
       tc_mbar_wait(&sm.bar_stage[b], b ? st.ph_stage1 : st.ph_stage0);

@@ -92,12 +92,13 @@ def test_packed_image_matches_descriptor_geometry_and_keeps_accuracy(tclib, tag,
     W1 = np.zeros((160, 16), dtype=np.float32)
     W1[:h1, :in1] = keep["w1"]
     W1[:h1, 15] = keep["b1"]
-    assert np.array_equal(read_operand(img, o_w1, 160, 16, lbo1, sbo, step1), W1)
-    assert np.array_equal(read_operand(img, o_w1lo, 160, 16, lbo1, sbo, step1), W1 - trunc_tf32(W1))
+    # operands are stored TF32-exact (hi = trunc, lo = trunc(w - hi)): the split does not depend on operand conversion
+    assert np.array_equal(read_operand(img, o_w1, 160, 16, lbo1, sbo, step1), trunc_tf32(W1))
+    assert np.array_equal(read_operand(img, o_w1lo, 160, 16, lbo1, sbo, step1), trunc_tf32(W1 - trunc_tf32(W1)))
     W2 = np.zeros((32, 160), dtype=np.float32)
     W2[:, :h1] = keep["w2"]
-    assert np.array_equal(read_operand(img, o_w2, 32, 160, lbo2, sbo, step2), W2)
-    assert np.array_equal(read_operand(img, o_w2lo, 32, 160, lbo2, sbo, step2), W2 - trunc_tf32(W2))
+    assert np.array_equal(read_operand(img, o_w2, 32, 160, lbo2, sbo, step2), trunc_tf32(W2))
+    assert np.array_equal(read_operand(img, o_w2lo, 32, 160, lbo2, sbo, step2), trunc_tf32(W2 - trunc_tf32(W2)))
     assert np.array_equal(img[o_b2 // 4:o_b2 // 4 + 32], keep["b2"]) and np.array_equal(img[o_w3 // 4:o_w3 // 4 + 32], keep["w3"])
     assert img[o_b3 // 4] == keep["b3"][0]
     if emb is not None:
