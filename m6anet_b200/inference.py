@@ -137,6 +137,29 @@ def plan_batches(n_reads: np.ndarray, lo: int, hi: int, reads_per_batch: int) ->
     return spans
 
 
+def append_file(out, path: str) -> None:
+    """Append the file at `path` at the current position of the open binary file `out`: in-kernel copy (sendfile) where
+    the platform allows it -- the shard files of a multi-GPU run are gigabytes of CSV --, a buffered copy otherwise
+    (sendfile refuses O_APPEND descriptors: open `out` with 'r+b' and seek to the end to get the fast path)."""
+    out.flush()
+    with open(path, 'rb') as part:
+        size = os.fstat(part.fileno()).st_size
+        sent = 0
+        try:
+            while sent < size:
+                n = os.sendfile(out.fileno(), part.fileno(), sent, min(size - sent, 1 << 30))
+                if n == 0:
+                    break
+                sent += n
+        except (OSError, AttributeError):     # sendfile unsupported for this pair of descriptors
+            pass
+        if sent < size:
+            part.seek(sent)
+            shutil.copyfileobj(part, out, 1 << 24)
+        elif sent:
+            out.seek(0, os.SEEK_END)       # keep the Python-level position in step with the descriptor
+
+
 def _resolve_device(device: str, local_rank: int, world: int) -> int:
     """--device -> CUDA device index (no torch import: the single-GPU path only needs the C ABI)."""
     from . import _cabi
@@ -261,10 +284,10 @@ def run_inference(model: MILModel, dl, args):
         dist.barrier()
         if rank == 0:    # concatenate the shard files in site order behind the headers
             for path in (site_path, indiv_path):
-                with open(path, 'ab') as out:
+                with open(path, 'r+b') as out:       # not 'ab': sendfile refuses O_APPEND descriptors
+                    out.seek(0, os.SEEK_END)
                     for r in range(world):
-                        with open(f"{path}.rank{r}", 'rb') as part:
-                            shutil.copyfileobj(part, out)
+                        append_file(out, f"{path}.rank{r}")
                         os.remove(f"{path}.rank{r}")
         dist.barrier()
     return site_prob, mod_count

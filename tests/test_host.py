@@ -562,3 +562,22 @@ def test_bind_host_to_device_is_best_effort(monkeypatch):
     fake.nvmlDeviceGetCpuAffinity = lambda h, n: [sum(1 << (c % 64) for c in allowed if c // 64 == w) for w in range(n)]
     monkeypatch.delenv("CUDA_VISIBLE_DEVICES")
     assert D.bind_host_to_device(0) == []                        # every CPU is local: single socket, nothing to do
+
+
+def test_append_file_concatenates_shards(tmp_path):
+    """Rank 0 concatenates the per-rank CSV shards behind the headers: in-kernel copy when the descriptor allows it
+    ('r+b'), buffered copy for an O_APPEND descriptor; later writes land behind the appended bytes either way."""
+    from m6anet_b200.inference import append_file
+    blob = os.urandom(3_000_001)
+    (tmp_path / "shard").write_bytes(blob)
+    (tmp_path / "empty").write_bytes(b"")
+    for mode in ("ab", "r+b"):
+        out_path = tmp_path / f"out_{mode}"
+        out_path.write_bytes(b"header\n")
+        with open(out_path, mode) as out:
+            out.seek(0, os.SEEK_END)
+            append_file(out, str(tmp_path / "shard"))
+            append_file(out, str(tmp_path / "empty"))
+            append_file(out, str(tmp_path / "shard"))
+            out.write(b"tail")
+        assert out_path.read_bytes() == b"header\n" + blob + blob + b"tail"
