@@ -9,7 +9,9 @@ accumulation, for the split variants
     3xTF32   a_hi*b_hi + a_lo*b_hi + a_hi*b_lo    (both split; the a_lo*b_lo term is dropped)
 and reports max |p - p_float64| per read next to the float32 CUDA-core formulation (the oracle).
 TF32 rounding = round-to-nearest-even to 10 explicit mantissa bits.  Accumulation inside the tensor core is modelled as
-float32 adds of exact products (an optimistic model: the hardware may truncate; the GPU run decides)."""
+float32 adds of exact products (an optimistic model: the hardware may truncate; the GPU run decides).  The last line is
+the pessimistic model of the kernel as written: operands truncated to TF32, and the accumulator rounded TOWARD ZERO to
+float32 after every K = 8 step of every term (20 steps x 3 terms for Linear-2)."""
 import os
 import sys
 
@@ -62,6 +64,40 @@ def main():
         zz = hh2.astype(np.float32) @ P.w3.reshape(-1) + P.b3[0]
         p = (1 / (1 + np.exp(-zz.astype(np.float32)))).astype(np.float32)
         print(f"{terms}xTF32: max|p - p64| = {np.abs(p - p64).max():.2e}   max|p - p_oracle32| = {np.abs(p - p32).max():.2e}")
+
+
+    # pessimistic model: truncation everywhere, round-toward-zero accumulation per MMA (K = 8) step
+    def tr(v):
+        v = np.ascontiguousarray(v, dtype=np.float32)
+        return (v.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32).reshape(v.shape)
+
+    def rz32(v64):
+        f = v64.astype(np.float32)
+        f = np.where(np.abs(f.astype(np.float64)) > np.abs(v64), np.nextafter(f, np.float32(0)), f)
+        return f.astype(np.float32)
+
+    def mm_rz(a, b):
+        ah, bh = tr(a), tr(b)
+        al, bl = tr(a - ah), tr(b - bh)
+        acc = np.zeros((a.shape[0], b.shape[0]), dtype=np.float32)
+        for k0 in range(0, a.shape[1], 8):
+            sl = slice(k0, k0 + 8)
+            for u, v in ((ah, bh), (al, bh), (ah, bl)):
+                acc = rz32(acc.astype(np.float64) + u[:, sl].astype(np.float64) @ v[:, sl].astype(np.float64).T)
+        return acc
+
+    xa = np.zeros((len(x), 16), dtype=np.float32)
+    xa[:, :15] = x.astype(np.float32)
+    xa[:, 15] = 1.0
+    w1a = np.zeros((160, 16), dtype=np.float32)
+    w1a[:150, :15] = w1f
+    w1a[:150, 15] = b1f
+    w2a = np.zeros((32, 160), dtype=np.float32)
+    w2a[:, :150] = P.w2
+    hh2 = mm_rz(np.maximum(mm_rz(xa, w1a), 0), w2a)
+    zz = np.maximum(hh2 + P.b2, 0) @ P.w3.reshape(-1) + P.b3[0]
+    p = (1 / (1 + np.exp(-zz.astype(np.float32)))).astype(np.float32)
+    print(f"3xTF32, truncated operands, accumulator rounded toward zero per K-step: max|p - p64| = {np.abs(p - p64).max():.2e}")
 
 
 if __name__ == "__main__":
