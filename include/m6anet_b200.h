@@ -126,7 +126,8 @@ int32_t m6a_auto_tile_reads(int64_t n_sites, int64_t total_reads, int32_t n_sms)
  *               (mod_ratio = mod_count / n_reads, formed by the host in float64 like np.mean)
  * scratch
  *   workspace   DEVICE buffer of at least m6a_mil_workspace_bytes(total_reads) bytes, 8-byte aligned, owned by the
- *               caller and private to this call until it has completed on `stream` (tile boundaries of the prepass).
+ *               caller and private to this call until it has completed on `stream` (tile boundaries of the prepass and
+ *               one tile-counter word).
  *               The library allocates nothing on this path.
  */
 int64_t m6a_mil_workspace_bytes(int64_t total_reads);

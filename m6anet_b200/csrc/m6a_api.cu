@@ -210,7 +210,7 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
   a.tile_reads = tile_reads;
   a.n_tiles = total_reads / tile_reads + 1;
   if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 7u)) return workspace ? M6A_EALIGN : M6A_EINVAL;
-  if (workspace_bytes < static_cast<int64_t>((a.n_tiles + 1) * sizeof(long long))) return M6A_EINVAL;
+  if (workspace_bytes < static_cast<int64_t>((a.n_tiles + 2) * sizeof(long long))) return M6A_EINVAL;   // bounds + tile counter
   long long* d_bounds = static_cast<long long*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   a.tile_bounds = d_bounds;
@@ -264,7 +264,7 @@ extern "C" int32_t m6a_auto_tile_reads(int64_t n_sites, int64_t total_reads, int
 
 extern "C" int64_t m6a_mil_workspace_bytes(int64_t total_reads) {
   if (total_reads < 0) return 0;
-  return (total_reads / 64 + 2) * static_cast<int64_t>(sizeof(long long));   // tiles hold >= 64 rows
+  return (total_reads / 64 + 3) * static_cast<int64_t>(sizeof(long long));   // tiles hold >= 64 rows: n_tiles + 1 bounds + 1 counter
 }
 
 extern "C" int m6a_sample_indices(uint64_t seed, int64_t site_id, int32_t n_reads, int32_t n_iters, int32_t n_samples,

@@ -284,7 +284,18 @@ mil_infer_kernel(const KernelArgs a, const BagArgs bags) {
   const bool tma_ok = a.feats_tma_ok;
   const float n_iters_f = static_cast<float>(a.n_iters);
 
+#if M6A_DYNAMIC_TILES
+  __shared__ long long s_next_tile;
+  unsigned long long* tile_counter = reinterpret_cast<unsigned long long*>(const_cast<long long*>(a.tile_bounds)) + a.n_tiles + 1;
+  for (;;) {
+   if (tid == 0) s_next_tile = static_cast<long long>(atomicAdd(tile_counter, 1ull));
+   __syncthreads();
+   const long long tile = s_next_tile;
+   __syncthreads();   // every thread has its copy before thread 0 draws the next tile
+   if (tile >= a.n_tiles) break;
+#else
   for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+#endif
    // a tile normally holds <= kSitesPerTileMax sites; more (very short sites) are taken in slices
    const long long tile_s0 = a.tile_bounds[tile], tile_s1 = a.tile_bounds[tile + 1];
    for (long long s0 = tile_s0; s0 < tile_s1; s0 += kSitesPerTileMax) {
@@ -529,6 +540,9 @@ __global__ void tile_bounds_kernel(const int64_t* __restrict__ read_off, long lo
   if (t > n_tiles) return;
   if (t == n_tiles) {
     tile_bounds[t] = n_sites;
+#if M6A_DYNAMIC_TILES
+    tile_bounds[t + 1] = 0;                  // the tile counter of mil_infer_kernel
+#endif
     return;
   }
   const long long target = t * tile_reads;

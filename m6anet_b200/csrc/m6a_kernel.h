@@ -28,6 +28,9 @@ namespace m6a {
 #ifndef M6A_WEIGHTS_CONST
 #define M6A_WEIGHTS_CONST 1   // 1: weight image as a __grid_constant__ kernel parameter (uniform datapath) instead of shared memory
 #endif
+#ifndef M6A_DYNAMIC_TILES
+#define M6A_DYNAMIC_TILES 0   // 1: CTAs take tiles from a global counter (workspace slot n_tiles + 1, zeroed by the prepass)
+#endif                        //    instead of striding by gridDim.x -- removes the tail imbalance of small / ragged shards
 #ifndef M6A_PAIR_UNROLL
 #define M6A_PAIR_UNROLL 5   // pair-loop unroll: deeper LDCU lookahead (1: 19.4 ms, 3: 18.36, 5: 18.35, 15: 17.8 but ragged 24.7)
 #endif

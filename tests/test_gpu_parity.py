@@ -246,7 +246,7 @@ def test_invalid_arguments_are_rejected(synthetic_inputs):
     ws = torch.empty(4, dtype=torch.int64, device="cuda:0")
     args = lambda wsp, wsb: (eng._handle, f.data_ptr(), off.data_ptr(), k.data_ptr(), 2, 40, 0, 20, 10, 0, None, 0.5,
                              rp.data_ptr(), sp.data_ptr(), mc.data_ptr(), wsp, wsb, None)
-    assert L.m6a_mil_workspace_bytes(40) == 16 and L.m6a_mil_workspace_bytes(10**6) >= (10**6 // 1000 + 2) * 8
+    assert L.m6a_mil_workspace_bytes(40) == 24 and L.m6a_mil_workspace_bytes(10**6) >= (10**6 // 1000 + 2) * 8
     assert L.m6a_mil_infer_f32(*args(None, 0)) == -1
     assert L.m6a_mil_infer_f32(*args(ws.data_ptr(), 8)) == -1
     assert L.m6a_mil_infer_f32(*args(ws.data_ptr(), 32)) == 0
