@@ -85,6 +85,18 @@ typedef struct {
 
 typedef struct m6a_model m6a_model_t; /* opaque: packed weight image resident on one device */
 
+/* Where the two Linear blocks of the read encoder run (results agree to float32 round-off, same index streams):
+ *   M6A_ENCODER_FFMA  CUDA cores, packed FFMA2 (mil_infer_kernel, m6anet_b200/csrc/m6a_kernel.cu)
+ *   M6A_ENCODER_TC    5th-generation tensor cores, tcgen05.mma kind::tf32 with error-compensated 3xTF32 operands and the
+ *                     accumulators in TMEM (mil_infer_tc_kernel, m6anet_b200/csrc/m6a_kernel_tc.cu); used for the
+ *                     inference entry points with n_samples == 20 and no explicit indices, the other calls (explicit
+ *                     indices, validate()-style bags, other bag sizes) run the FFMA kernel whatever the setting. */
+#define M6A_ENCODER_FFMA 0
+#define M6A_ENCODER_TC 1
+#ifndef M6A_ENCODER_DEFAULT
+#define M6A_ENCODER_DEFAULT M6A_ENCODER_TC
+#endif
+
 int m6a_version(void);
 const char *m6a_strerror(int status);
 /* Thin wrappers of cudaGetDeviceCount / cudaSetDevice so that a host program needs no other CUDA binding. */
@@ -95,6 +107,20 @@ int m6a_set_device(int32_t device);
  * device (synchronous).  The model may be used from any stream of that device. */
 int m6a_model_create(const m6a_weights_t *w, m6a_model_t **out);
 int m6a_model_destroy(m6a_model_t *model);
+/* Selects the read-encoder implementation of this model (M6A_ENCODER_*); the environment variable M6A_ENCODER=ffma|tc
+ * overrides the default at m6a_model_create.  M6A_EUNSUPPORTED when the model does not fit the tensor-core image
+ * (emb_dim > 2 or h1 > 160).  m6a_model_get_encoder returns the implementation in effect. */
+int m6a_model_set_encoder(m6a_model_t *model, int32_t encoder);
+int m6a_model_get_encoder(const m6a_model_t *model);
+/* Debug aid: arms (first call) and reads the trap record of the tensor-core kernel -- {wait site, block, thread, parity}
+ * of a bounded mbarrier wait that gave up, kept in mapped host memory so that it survives the trap. */
+int m6a_debug_trap_record(m6a_model_t *model, int32_t *out4);
+/* Page-locked host memory (cudaHostAlloc, portable) for the host-buffer entry points: the H2D / D2H copies of
+ * m6a_mil_infer_host_f32 only overlap with the kernel when its buffers are pinned. */
+int m6a_pinned_alloc(void **out, int64_t bytes);
+int m6a_pinned_free(void *p);
+/* One-line description of the kernels this build ships. */
+const char *m6a_build_info(void);
 /* Feature rows per tile of the device call, 64..4096; 0 (default) = automatic: a multiple of the site depth close to
  * 1000 rows (500 for small jobs).  Tiles are read-balanced: tile t holds the sites whose first row is in [t*T, (t+1)*T). */
 int m6a_model_set_tile_reads(m6a_model_t *model, int32_t tile_reads);
@@ -137,6 +163,15 @@ int m6a_mil_infer_f32(const m6a_model_t *model, const float *feats, const int64_
                       const uint16_t *sample_idx, float read_threshold, float *read_prob,
                       float *site_prob, int32_t *mod_count, void *workspace, int64_t workspace_bytes,
                       void *stream);
+
+/* m6a_mil_infer_f32 without explicit indices, writing the two per-site outputs INTERLEAVED into one buffer
+ * site_out [n_sites][2] 32-bit words (word 0 = site probability float32, word 1 = mod_count int32; 8-byte aligned):
+ * the send buffer of the one all-gather of a multi-GPU run, so no pack kernels run. */
+int m6a_mil_infer_packed_f32(const m6a_model_t *model, const float *feats, const int64_t *read_off,
+                             const int32_t *kmer_idx, int64_t n_sites, int64_t total_reads,
+                             int64_t site_id_base, int32_t n_samples, int32_t n_iters, uint64_t seed,
+                             float read_threshold, float *read_prob, void *site_out, void *workspace,
+                             int64_t workspace_bytes, void *stream);
 
 /*
  * Same computation with HOST buffers (read_off[0] must be 0 here).  Sites are cut into

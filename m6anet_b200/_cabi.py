@@ -16,7 +16,8 @@ CSRC = os.path.join(_HERE, "csrc")
 
 EXPORTS = (
     "m6a_version", "m6a_strerror", "m6a_device_count", "m6a_set_device", "m6a_model_create", "m6a_model_destroy", "m6a_model_set_tile_reads", "m6a_auto_tile_reads", "m6a_mil_workspace_bytes",
-    "m6a_mil_infer_f32",
+    "m6a_mil_infer_f32", "m6a_mil_infer_packed_f32", "m6a_model_set_encoder", "m6a_model_get_encoder", "m6a_debug_trap_record",
+    "m6a_pinned_alloc", "m6a_pinned_free", "m6a_build_info",
     "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_mil_validate_f32", "m6a_mil_validate_host_f32", "m6a_sample_bags",
     "m6a_last_launch", "m6a_ingest_parts", "m6a_info_count", "m6a_info_read",
     "m6a_write_site_csv",
@@ -86,6 +87,20 @@ def lib() -> C.CDLL:
     L.m6a_model_set_tile_reads.argtypes = [vp, i32]
     L.m6a_mil_infer_f32.restype = C.c_int
     L.m6a_mil_infer_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, u64, vp, f32, vp, vp, vp, vp, i64, vp]
+    L.m6a_mil_infer_packed_f32.restype = C.c_int
+    L.m6a_mil_infer_packed_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, u64, f32, vp, vp, vp, i64, vp]
+    L.m6a_model_set_encoder.restype = C.c_int
+    L.m6a_model_set_encoder.argtypes = [vp, i32]
+    L.m6a_model_get_encoder.restype = C.c_int
+    L.m6a_model_get_encoder.argtypes = [vp]
+    L.m6a_debug_trap_record.restype = C.c_int
+    L.m6a_debug_trap_record.argtypes = [vp, vp]
+    L.m6a_pinned_alloc.restype = C.c_int
+    L.m6a_pinned_alloc.argtypes = [C.POINTER(vp), i64]
+    L.m6a_pinned_free.restype = C.c_int
+    L.m6a_pinned_free.argtypes = [vp]
+    L.m6a_build_info.restype = C.c_char_p
+    L.m6a_build_info.argtypes = []
     L.m6a_auto_tile_reads.restype = i32
     L.m6a_auto_tile_reads.argtypes = [i64, i64, i32]
     L.m6a_mil_workspace_bytes.restype = i64
@@ -144,3 +159,36 @@ def parse_device(device) -> int:
 def check(status: int, where: str) -> None:
     if status != 0:
         raise M6AError(status, where)
+
+
+ENCODERS = {"ffma": 0, "tc": 1}     # M6A_ENCODER_FFMA / M6A_ENCODER_TC
+
+
+class _PinnedOwner:
+    """Keeps one cudaHostAlloc block alive for the NumPy array that views it."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.m6a_pinned_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> "_np.ndarray":
+    """np.empty in page-locked host memory (m6a_pinned_alloc): the H2D / D2H copies of the host-buffer entry points only
+    overlap with the kernel when their buffers are pinned.  The array (and every view of it) keeps the block alive."""
+    dtype = _np.dtype(dtype)
+    shape = (shape,) if isinstance(shape, (int, _np.integer)) else tuple(int(x) for x in shape)
+    n_bytes = int(_np.prod(shape, dtype=_np.int64)) * dtype.itemsize
+    if n_bytes == 0:
+        return _np.empty(shape, dtype=dtype)
+    p = C.c_void_p()
+    check(lib().m6a_pinned_alloc(C.byref(p), n_bytes), "m6a_pinned_alloc")
+    owner = _PinnedOwner(p)
+    buf = (C.c_char * n_bytes).from_address(p.value)
+    buf._owner = owner                                    # the ctypes buffer is the base object of the array
+    return _np.frombuffer(buf, dtype=dtype).reshape(shape)

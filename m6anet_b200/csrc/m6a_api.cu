@@ -33,6 +33,9 @@ struct m6a_model {
   WeightImage host_image;        // packed weights, host copy (kernel-parameter path)
   void* d_image;
   void* d_ctab;
+  void* d_tc_image = nullptr;    // tcx::WeightImageTc (tensor-core read encoder), nullptr when the model does not fit it
+  int encoder = M6A_ENCODER_DEFAULT;
+  int* trap_record = nullptr;    // mapped host memory: which bounded wait of the tensor-core kernel gave up (debug)
   int device;
   int n_sms;
   int tile_reads = 0;            // feature rows per tile; 0 = automatic (m6a_model_set_tile_reads)
@@ -119,9 +122,51 @@ extern "C" int m6a_model_create(const m6a_weights_t* w, m6a_model_t** out) {
         ctab[(static_cast<size_t>(t) * n_kmer + k) * kH1Max + j] = c;
       }
 
+  // tensor-core image: RN_tf32 split of [w1 | b1] and of w2 (m6a_layout.h); emb_dim 0..2, h1 <= 160
+  tcx::WeightImageTc* tci = nullptr;
+  if (E <= 2 && h1 <= tcx::kN1 && n_kmer * std::max(E, 1) <= tcx::kEmbMax) {
+    tci = static_cast<tcx::WeightImageTc*>(calloc(1, sizeof(tcx::WeightImageTc)));
+    if (!tci) {
+      free(img);
+      return M6A_ENOMEM;
+    }
+    auto rn_tf32 = [](float f) {
+      uint32_t u;
+      memcpy(&u, &f, 4);
+      u = (u + 0x1000u) & 0xFFFFE000u;
+      memcpy(&f, &u, 4);
+      return f;
+    };
+    for (int j = 0; j < h1; ++j)
+      for (int k = 0; k < tcx::kK1; ++k) {
+        float v = 0.0f;
+        if (k < in1) v = w->w1[static_cast<size_t>(j) * in1 + k];
+        else if (k == tcx::kK1 - 1) v = w->b1[j];
+        const float hi = rn_tf32(v);
+        tci->w1hi[k / 4][j][k % 4] = hi;
+        tci->w1lo[k / 4][j][k % 4] = rn_tf32(v - hi);
+      }
+    for (int n = 0; n < kH2; ++n)
+      for (int k = 0; k < h1; ++k) {
+        const float v = w->w2[static_cast<size_t>(n) * h1 + k];
+        const float hi = rn_tf32(v);
+        tci->w2s[k / 4][n][k % 4] = hi;
+        tci->w2s[k / 4][kH2 + n][k % 4] = rn_tf32(v - hi);
+      }
+    for (int k = 0; k < kH2; ++k) {
+      tci->b2[k] = w->b2[k];
+      tci->w3[k] = w->w3[k];
+    }
+    tci->b3 = w->b3[0];
+    tci->emb_dim = E;
+    tci->n_kmer = n_kmer;
+    for (int i = 0; i < n_kmer * E; ++i) tci->emb[i] = w->emb[i];
+  }
+
   m6a_model* m = new (std::nothrow) m6a_model();
   if (!m) {
     free(img);
+    free(tci);
     return M6A_ENOMEM;
   }
   cudaError_t e = cudaGetDevice(&m->device);
@@ -132,9 +177,17 @@ extern "C" int m6a_model_create(const m6a_weights_t* w, m6a_model_t** out) {
   if (e == cudaSuccess) e = cudaMalloc(&m->d_ctab, ctab.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(m->d_image, img, sizeof(WeightImage), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(m->d_ctab, ctab.data(), ctab.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && tci) e = cudaMalloc(&m->d_tc_image, sizeof(tcx::WeightImageTc));
+  if (e == cudaSuccess && tci) e = cudaMemcpy(m->d_tc_image, tci, sizeof(tcx::WeightImageTc), cudaMemcpyHostToDevice);
   m->host_image = *img;
   free(img);
+  free(tci);
+  if (const char* env = getenv("M6A_ENCODER")) {      // build-independent A/B switch: "ffma" | "tc"
+    if (!strcmp(env, "ffma")) m->encoder = M6A_ENCODER_FFMA;
+    else if (!strcmp(env, "tc")) m->encoder = M6A_ENCODER_TC;
+  }
   if (e != cudaSuccess) {
+    if (m->d_tc_image) cudaFree(m->d_tc_image);
     if (m->d_image) cudaFree(m->d_image);
     if (m->d_ctab) cudaFree(m->d_ctab);
     delete m;
@@ -156,11 +209,68 @@ extern "C" int m6a_model_set_tile_reads(m6a_model_t* model, int32_t tile_reads) 
   return M6A_OK;
 }
 
+extern "C" int m6a_model_set_encoder(m6a_model_t* model, int32_t encoder) {
+  if (!model || (encoder != M6A_ENCODER_FFMA && encoder != M6A_ENCODER_TC)) return M6A_EINVAL;
+  if (encoder == M6A_ENCODER_TC && !model->d_tc_image) return M6A_EUNSUPPORTED;
+  model->encoder = encoder;
+  return M6A_OK;
+}
+
+extern "C" int m6a_model_get_encoder(const m6a_model_t* model) {
+  if (!model) return M6A_EINVAL;
+  return (model->encoder == M6A_ENCODER_TC && model->d_tc_image) ? M6A_ENCODER_TC : M6A_ENCODER_FFMA;
+}
+
+// Debug aid of the tensor-core kernel: every mbarrier wait is bounded; when one gives up it records
+// {wait site, block, thread, parity} in mapped host memory before it traps, readable after the context is lost.
+extern "C" int m6a_debug_trap_record(m6a_model_t* model, int32_t* out4) {
+  if (!model) return M6A_EINVAL;
+  if (!model->trap_record) {
+    M6A_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&model->trap_record), 64, cudaHostAllocMapped));
+    memset(model->trap_record, 0, 64);
+    int* dptr = nullptr;
+    M6A_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), model->trap_record, 0));
+    M6A_CUDA(tc_set_trap_record(dptr));
+  }
+  if (out4)
+    for (int i = 0; i < 4; ++i) out4[i] = model->trap_record[i];
+  return M6A_OK;
+}
+
+// Debug aid (builds with -DM6A_TC_PROFILE=1): cycles per phase of one thread per role of block 0 of the last launch.
+extern "C" int m6a_debug_tc_profile(uint64_t* out32) {
+  if (!out32) return M6A_EINVAL;
+  M6A_CUDA(cudaDeviceSynchronize());
+  M6A_CUDA(tc_read_profile(reinterpret_cast<unsigned long long*>(out32)));
+  return M6A_OK;
+}
+
+extern "C" int m6a_pinned_alloc(void** out, int64_t bytes) {
+  if (!out || bytes < 0) return M6A_EINVAL;
+  *out = nullptr;
+  if (bytes == 0) return M6A_OK;
+  const cudaError_t e = cudaHostAlloc(out, static_cast<size_t>(bytes), cudaHostAllocPortable);
+  return e == cudaSuccess ? M6A_OK : static_cast<int>(e);
+}
+
+extern "C" int m6a_pinned_free(void* p) {
+  if (!p) return M6A_OK;
+  const cudaError_t e = cudaFreeHost(p);
+  return e == cudaSuccess ? M6A_OK : static_cast<int>(e);
+}
+
+extern "C" const char* m6a_build_info(void) {
+  return "m6anet_b200 r2: mil_infer_tc_kernel<20> (tcgen05 3xTF32 encoder, warp-specialised, 1 CTA/SM) + "
+         "mil_infer_kernel<NS,BAGS> (FFMA2 encoder, dynamic tiles)";
+}
+
 extern "C" int m6a_model_destroy(m6a_model_t* model) {
   if (!model) return M6A_OK;
   m6a_release_workspace(model);
   cudaFree(model->d_image);
   cudaFree(model->d_ctab);
+  cudaFree(model->d_tc_image);
+  if (model->trap_record) cudaFreeHost(model->trap_record);
   delete model;
   return M6A_OK;
 }
@@ -179,11 +289,24 @@ static int auto_tile_reads(long long n_sites, long long total_reads, int n_sms) 
   return static_cast<int>(std::max<long long>(64, std::min<long long>(base, kQCap)));
 }
 
+// Rows per tile for the tensor-core kernel: slabs are slices of <= 64 sites, encoded 128 rows at a time, so a tile of
+// 64 sites' worth of rows (a multiple of 128 for every even site depth) wastes no MMA rows; <= 4096 rows (q table).
+static int auto_tile_reads_tc(long long n_sites, long long total_reads) {
+  long long base = 2048;
+  if (n_sites > 0 && total_reads % n_sites == 0) {
+    const long long depth = total_reads / n_sites;
+    if (depth >= 1 && depth * kSitesPerTileMax <= kQCap) base = depth * kSitesPerTileMax;
+    else if (depth >= 1 && depth <= kQCap) base = (kQCap / depth) * depth;
+  }
+  return static_cast<int>(std::max<long long>(64, std::min<long long>(base, kQCap)));
+}
+
 static int infer_device_impl(const m6a_model_t* model, int tile_reads, const float* feats, const int64_t* read_off,
                              const int32_t* kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
                              int32_t n_samples, int32_t n_iters, uint64_t seed, const uint16_t* sample_idx,
                              float read_threshold, float* read_prob, float* site_prob, int32_t* mod_count,
-                             void* workspace, int64_t workspace_bytes, void* stream, const BagArgs* bags = nullptr) {
+                             void* workspace, int64_t workspace_bytes, void* stream, const BagArgs* bags = nullptr,
+                             int site_stride = 1) {
   if (!model || n_sites < 0 || total_reads < 0) return M6A_EINVAL;
   if (n_samples < 1 || n_samples > kMaxSamples || n_iters < 1) return M6A_EINVAL;
   if (bags && (bags->pool < kPoolProd || bags->pool > kPoolMax || (bags->replace != 0 && bags->replace != 1))) return M6A_EINVAL;
@@ -206,8 +329,13 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
   a.n_sites = n_sites;
   // read-balanced tiles: tile t = sites whose first row lies in [t*T, (t+1)*T); boundaries by a prepass into the
   // caller's workspace (the library allocates nothing on this path)
-  if (tile_reads <= 0) tile_reads = auto_tile_reads(n_sites, total_reads, model->n_sms);
+  const bool use_tc = model->encoder == M6A_ENCODER_TC && model->d_tc_image != nullptr && bags == nullptr &&
+                      sample_idx == nullptr && n_samples == 20;
+  if (tile_reads <= 0 || (use_tc && model->tile_reads <= 0)) {
+    tile_reads = use_tc ? auto_tile_reads_tc(n_sites, total_reads) : auto_tile_reads(n_sites, total_reads, model->n_sms);
+  }
   a.tile_reads = tile_reads;
+  a.site_stride = site_stride;
   a.n_tiles = total_reads / tile_reads + 1;
   if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 7u)) return workspace ? M6A_EALIGN : M6A_EINVAL;
   if (workspace_bytes < static_cast<int64_t>((a.n_tiles + 2) * sizeof(long long))) return M6A_EINVAL;   // bounds + tile counter
@@ -225,7 +353,10 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
 
   LaunchInfo info;
   cudaError_t e = launch_tile_bounds(read_off, n_sites, a.n_tiles, tile_reads, d_bounds, st);
-  if (e == cudaSuccess) e = launch_mil_infer(a, &model->host_image, bags, model->n_sms, st, &info);
+  if (e == cudaSuccess) {
+    e = use_tc ? launch_mil_infer_tc(a, static_cast<const tcx::WeightImageTc*>(model->d_tc_image), model->n_sms, st, &info)
+               : launch_mil_infer(a, &model->host_image, bags, model->n_sms, st, &info);
+  }
   if (e != cudaSuccess) return static_cast<int>(e);
   g_last = info;
   g_last_launches = 2;   // tile_bounds_kernel + mil_infer_kernel
@@ -241,6 +372,18 @@ extern "C" int m6a_mil_infer_f32(const m6a_model_t* model, const float* feats, c
   return infer_device_impl(model, model->tile_reads, feats, read_off, kmer_idx, n_sites, total_reads, site_id_base, n_samples,
                            n_iters, seed, sample_idx, read_threshold, read_prob, site_prob, mod_count, workspace,
                            workspace_bytes, stream);
+}
+
+extern "C" int m6a_mil_infer_packed_f32(const m6a_model_t* model, const float* feats, const int64_t* read_off,
+                                        const int32_t* kmer_idx, int64_t n_sites, int64_t total_reads, int64_t site_id_base,
+                                        int32_t n_samples, int32_t n_iters, uint64_t seed, float read_threshold,
+                                        float* read_prob, void* site_out, void* workspace, int64_t workspace_bytes,
+                                        void* stream) {
+  if (!model || (n_sites > 0 && !site_out)) return M6A_EINVAL;
+  if (reinterpret_cast<uintptr_t>(site_out) & 7u) return M6A_EALIGN;
+  return infer_device_impl(model, model->tile_reads, feats, read_off, kmer_idx, n_sites, total_reads, site_id_base, n_samples,
+                           n_iters, seed, nullptr, read_threshold, read_prob, static_cast<float*>(site_out),
+                           static_cast<int32_t*>(site_out) + 1, workspace, workspace_bytes, stream, nullptr, 2);
 }
 
 // validate()-style literal MIL forward (reference utils/training_utils.py:213-268): same read encoder, phase B pools one

@@ -523,8 +523,9 @@ mil_infer_kernel(const KernelArgs a, const BagArgs bags) {
       const int n = sm.roff[tid + 1] - sm.roff[tid];
       float s = 0.0f;
       for (int k = 0; k < n_blocks; ++k) s += sm.partial[tid][k];
-      a.site_prob[s0 + tid] = n > 0 ? s / n_iters_f : __int_as_float(0x7fc00000);
-      a.mod_count[s0 + tid] = sm.cnt[tid];
+      const size_t o = static_cast<size_t>(s0 + tid) * a.site_stride;
+      a.site_prob[o] = n > 0 ? s / n_iters_f : __int_as_float(0x7fc00000);
+      a.mod_count[o] = sm.cnt[tid];
     }
     __syncthreads();  // roff/cnt/partial are rewritten by the next tile
    }

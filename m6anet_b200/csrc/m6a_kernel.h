@@ -71,6 +71,7 @@ struct KernelArgs {
   unsigned long long feats_bytes;
   unsigned long long seed;
   int tile_reads;      // target feature rows per tile
+  int site_stride;     // 32-bit words between consecutive sites in site_prob / mod_count (1; 2 = interleaved in one buffer)
   int n_samples;
   int n_iters;
   int n_blocks;        // ceil(n_iters / (32 * iters_per_lane)) <= 64
@@ -97,6 +98,11 @@ size_t smem_bytes();
 // bags == nullptr: inference (Monte-Carlo noisy-OR with replacement); otherwise the validate()-style bags instantiation
 cudaError_t launch_mil_infer(const KernelArgs& a, const WeightImage* host_image, const BagArgs* bags, int n_sms,
                              cudaStream_t stream, LaunchInfo* info);
+// the tensor-core kernel (m6a_kernel_tc.cu): inference stream, n_samples == 20; n_sms CTAs of 512 threads
+cudaError_t launch_mil_infer_tc(const KernelArgs& a, const tcx::WeightImageTc* d_image, int n_sms, cudaStream_t stream,
+                                LaunchInfo* info);
+cudaError_t tc_set_trap_record(int* mapped_device_ptr);
+cudaError_t tc_read_profile(unsigned long long* out32);   // zeros unless built with -DM6A_TC_PROFILE=1
 cudaError_t launch_tile_bounds(const int64_t* read_off, long long n_sites, long long n_tiles, int tile_reads,
                                long long* tile_bounds, cudaStream_t stream);
 // without_replacement: the Floyd bag stream instead of the inference stream

@@ -1,0 +1,676 @@
+// Fused MIL-inference kernel for sm_100a with the read encoder on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Same contract and the same results (index streams, summation order) as mil_infer_kernel (m6a_kernel.cu); what changes is
+// WHERE the work runs.  ncu of the CUDA-core kernel: DRAM 1.4 % busy, FMA pipe 65 % -- the path is bound by FP32 issue, and
+// 11.4 of its 17.5 ms per pass are the two Linear blocks (profiles/r02_tiles_static_1m_it1.json).  Here they are two
+// tcgen05.mma chains per tile of 128 reads (error-compensated 3xTF32, m6a_layout.h), and the CUDA cores keep only the
+// relu / operand split, the sigmoid and the Monte-Carlo pooling.
+//
+// One persistent CTA per SM, 768 threads, warp-specialised; the roles run concurrently on DIFFERENT slabs
+// (slab = the <= 64 consecutive sites of one slice of a read-balanced tile, as in m6a_kernel.cu):
+//   warp 1        MMA issuer (one elected lane): Linear-1 of tile t+1 (6 MMAs M128 N160 K8, A and B from shared memory),
+//                 then per 32-column chunk of tile t: 8 MMAs (A from TMEM: N64 main|correction + N32 correction)
+//   warps 4..11   encoder epilogue, two per TMEM lane quadrant (each takes 16 of a chunk's 32 columns), thread = read:
+//                   X     gather [x(9) | emb(6) | 1] of tile t+1 -> RN_tf32 split -> shared memory (UMMA K-major layout)
+//                   E1    per chunk: tcgen05.ld D1 -> relu -> hi/lo split -> tcgen05.st hi IN PLACE (A operand of Linear-2)
+//                         and lo into a 2-slot staging ring -> mbarrier -> MMA issuer
+//                   E2    tile t-1: tcgen05.ld D2 (main + correction) -> +b2, relu, . w3, sigmoid -> read_prob (HBM),
+//                         q = 1 - p (shared memory of the slab slot), threshold count; last tile of a slab -> slab_full
+//   warps 0,2,3,12..23  Monte-Carlo pooling of a FINISHED slab (m6a_mc.cuh: warp per (site, block of 256 iterations),
+//                 Philox-seeded MWC64X lane streams), then site_prob / mod_count and slab_empty
+// TMEM (512 columns): D1[2] 2 x 160 | A_lo ring 2 x 32 | D2[2] 2 x (32 main + 32 correction).
+// Every mbarrier wait is bounded (a lost arrival traps instead of hanging the GPU).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "m6a_kernel.h"
+#include "m6a_mc.cuh"
+#include "m6a_rng.cuh"
+#include "m6a_tc.cuh"
+
+namespace m6a {
+namespace tcx {
+
+using namespace m6a::tc;
+
+constexpr int kTcThreads = 1024;
+constexpr int kMmaWarp = 1;
+constexpr int kE1Warp0 = 4;                  // warps 4..11 : E1 (relu / split), two per TMEM lane quadrant (quadrant = warp % 4)
+constexpr int kSeWarp0 = 12;                 // warps 12..19: staging of X + E2 (sigmoid, outputs), two per quadrant
+constexpr int kRoleWarps = 8;
+constexpr int kRoleThreads = kRoleWarps * 32;   // 256
+constexpr int kMcWarps = 15;                 // warps 0, 2, 3, 20..31
+constexpr int kMcThreads = kMcWarps * 32;
+constexpr int kMcChains = 4;                 // (site, block) items a Monte-Carlo warp interleaves
+constexpr int kSlots = 3;                    // slab slots in shared memory (q table, offsets, counters, partial sums)
+constexpr int kSlabSites = kSitesPerTileMax; // 64
+constexpr int kTmemCols = 512;
+constexpr uint32_t kColD1 = 0, kColALo = 2 * kN1, kColD2 = 2 * kN1 + 2 * kChunk;   // 0 | 320 | 384
+static_assert(kColD2 + 2 * 2 * kN2 == kTmemCols, "TMEM column budget");
+constexpr int kBarSe = 1, kBarMc = 2;        // named barriers
+constexpr int kHalfCols = kChunk / 2;        // columns of a chunk per warp
+constexpr int kCtrlRing = 8;                 // per-tile control words (the staging warps run at most 4 tiles ahead of E1)
+
+// UMMA operand geometry (byte offsets the descriptors carry; see make_desc)
+constexpr uint32_t kSbo = 128;
+constexpr uint32_t kLboX = kTileM * 16, kStepX = 2 * kLboX;
+constexpr uint32_t kLboW1 = kN1 * 16, kStepW1 = 2 * kLboW1;
+constexpr uint32_t kLboW2 = 2 * kN2 * 16, kStepW2 = 2 * kLboW2;
+
+struct SlabMeta {
+  long long s0;      // first site of the slab (shard-local)
+  long long r0;      // first feature row
+  int ns, nr;        // sites, rows
+  int stop;          // 1: no more slabs for this CTA
+  int pad;
+};
+
+struct alignas(128) TcSmem {
+  float w1hi[kK1 / 4][kN1][4];                  // 10 KB   B of Linear-1
+  float w1lo[kK1 / 4][kN1][4];                  // 10 KB
+  float w2s[kN1 / 4][2 * kN2][4];               // 40 KB   B of Linear-2 (rows 0..31 hi, 32..63 lo)
+  float x[2][2][kK1 / 4][kTileM][4];            // 32 KB   A of Linear-1: [buffer][hi, lo][k-chunk][row][4]
+  float fbuf[2][kTileM][kK1];                   // 16 KB   prefetched inputs of the next tile (cp.async), [x(9) | emb | 1]
+  float q[kSlots][kQCap];                       // 48 KB   q = 1 - p of a slab
+  float zpart[2][kTileM];                       // partial logits of the second half of the outputs
+  float b2[kN2];
+  float w3[kN2];
+  float b3;
+  uint32_t tmem_base;
+  int x_ctrl[kCtrlRing];                        // per tile: 1 = staged, 0 = stop (written before the x_full arrivals)
+  long long next_tile;                          // broadcast of the dynamic tile counter
+  SlabMeta meta[kSlots];
+  int roff[kSlots][kSlabSites + 1];
+  int cnt[kSlots][kSlabSites];
+  int kid[kSlots][kSlabSites][kKmerPos];
+  alignas(8) unsigned long long x_full[2];      // staging (256) -> MMA, E1 : operand X[b] staged
+  alignas(8) unsigned long long l1_done[2];     // MMA commit    -> E1, staging : D1[b] ready / X[b] consumed
+  alignas(8) unsigned long long a_full[2];      // E1 (256)      -> MMA : chunk staged in D1 (hi) / A_lo slot
+  alignas(8) unsigned long long a_free[2];      // MMA commit    -> E1 : A_lo slot consumed
+  alignas(8) unsigned long long d2_full[2];     // MMA commit    -> E2 : D2[j] complete
+  alignas(8) unsigned long long d2_free[2];     // E2 (256)      -> MMA : D2[j] read out
+  alignas(8) unsigned long long slab_full[kSlots];   // E2 (128) -> MC
+  alignas(8) unsigned long long slab_empty[kSlots];  // MC (1)   -> staging
+  // float partial[kSlots][kSlabSites][n_blocks] follows (dynamic)
+};
+static_assert(offsetof(TcSmem, w1lo) % 128 == 0 && offsetof(TcSmem, w2s) % 128 == 0 && offsetof(TcSmem, x) % 128 == 0,
+              "UMMA operands must start on a 128-byte core-matrix boundary");
+static_assert(offsetof(TcSmem, w1hi) == 0 && offsetof(TcSmem, w2s) + sizeof(float) * kN1 / 4 * 2 * kN2 * 4 == kTcOperandBytes,
+              "operand block is one contiguous copy of the image head");
+
+size_t tc_smem_bytes(int n_blocks) {
+  return sizeof(TcSmem) + static_cast<size_t>(kSlots) * kSlabSites * n_blocks * sizeof(float);
+}
+
+// ---- optional phase profile (-DM6A_TC_PROFILE=1): cycles per phase of one thread per role of block 0 ------------------------
+#ifndef M6A_TC_PROFILE
+#define M6A_TC_PROFILE 0
+#endif
+#if M6A_TC_PROFILE
+__device__ unsigned long long g_prof[40];
+#define PROF_DECL unsigned long long prof_t0 = clock64(); unsigned long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF(i) do { const unsigned long long prof_t1 = clock64(); prof_acc[i] += prof_t1 - prof_t0; prof_t0 = prof_t1; } while (0)
+#define PROF_STORE(base, cond) do { if ((cond) && blockIdx.x == 0) for (int pi = 0; pi < 10; ++pi) g_prof[(base) + pi] = prof_acc[pi]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_STORE(base, cond)
+#endif
+
+// ---- ablation switches for timing experiments only (results are WRONG when any is set) ---------------------------------------
+#ifndef M6A_ABL
+#define M6A_ABL 0      // bit 0: no proxy fence; 1: E1 without TMEM traffic / math; 2: no MMAs issued; 3: E2 without TMEM load / math;
+#endif                 // bit 4: staging without cp.async / split; 5: MC items skipped
+
+// wait sites (trap record)
+enum WaitSite : int {
+  kWaitXFull = 1, kWaitL1Done, kWaitAFull, kWaitAFree, kWaitD2Full, kWaitD2Free, kWaitSlabFull, kWaitSlabEmpty,
+  kWaitXFullE1, kWaitL1DoneSe
+};
+
+struct TileInfo {      // one MMA tile of 128 rows, as seen by the staging / E2 thread that owns row `row`
+  long long grow;      // global feature row of this thread
+  int slot;            // slab slot
+  int lr;              // slab-local row
+  int site_l;          // slab-local site of the row
+  bool exists, valid, last;
+};
+
+__device__ __forceinline__ float rn_tf32(float v) {     // round to nearest (ties away), low 13 mantissa bits zero
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kTcThreads, 1)
+mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
+  float* partial_base = reinterpret_cast<float*>(smem_raw + sizeof(TcSmem));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_blocks = a.n_blocks, ipl = a.iters_per_lane;
+
+  // ---- one-time setup: operands -> shared memory, barriers, TMEM -----------------------------------------------------------
+  {
+    const float4* src = reinterpret_cast<const float4*>(image);
+    float4* dst = reinterpret_cast<float4*>(&sm.w1hi[0][0][0]);
+    for (int i = tid; i < kTcOperandBytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
+    if (tid < kN2) {
+      sm.b2[tid] = image->b2[tid];
+      sm.w3[tid] = image->w3[tid];
+    }
+    if (tid == 0) {
+      sm.b3 = image->b3;
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sm.x_full[i], kRoleThreads);
+        mbar_init(&sm.l1_done[i], 1);
+        mbar_init(&sm.a_full[i], kRoleThreads);
+        mbar_init(&sm.a_free[i], 1);
+        mbar_init(&sm.d2_full[i], 1);
+        mbar_init(&sm.d2_free[i], kRoleThreads);
+      }
+      for (int i = 0; i < kSlots; ++i) {
+        mbar_init(&sm.slab_full[i], kTileM);
+        mbar_init(&sm.slab_empty[i], 1);
+      }
+      fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, kTmemCols);
+    fence_proxy_async();
+    fence_before();
+    __syncthreads();
+    fence_after();
+  }
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == kMmaWarp) {
+    // ======================================== MMA issuer ===================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc(kTileM, kN1), idesc64 = make_idesc(kTileM, 2 * kN2), idesc32 = make_idesc(kTileM, kN2);
+      // descriptors differ only in the start-address field (bits [0,14) = address >> 4): build once, add offsets
+      const uint64_t dx0 = make_desc(smem_u32(sm.x[0][0]), kLboX, kSbo);
+      const uint64_t dw1hi = make_desc(smem_u32(sm.w1hi), kLboW1, kSbo), dw1lo = make_desc(smem_u32(sm.w1lo), kLboW1, kSbo);
+      const uint64_t dw2 = make_desc(smem_u32(sm.w2s), kLboW2, kSbo);
+      constexpr uint64_t kXBuf = sizeof(sm.x[0]) >> 4, kXLo = sizeof(sm.x[0][0]) >> 4;
+      uint32_t g = 0;                     // chunk counter (A_lo slot = g & 1)
+      bool stop = false;
+      PROF_DECL;
+      for (uint32_t t = 0;; ++t) {
+        const uint32_t b = t & 1u;
+        // ---- Linear-1 of tile t ------------------------------------------------------------------------------------------
+        if (!stop) {
+          mbar_wait(&sm.x_full[b], (t >> 1) & 1u, kWaitXFull);
+          stop = sm.x_ctrl[t % kCtrlRing] == 0;
+        }
+        PROF(0);
+        if (!stop) {
+          fence_after();
+          const uint64_t ax = dx0 + b * kXBuf, axlo = ax + kXLo;
+          const uint32_t d1 = tmem + kColD1 + b * kN1;
+          if (!(M6A_ABL & 4)) {
+          mma_ss(d1, ax, dw1hi, idesc1, 0u);
+          mma_ss_acc(d1, axlo, dw1hi, idesc1);
+          mma_ss_acc(d1, ax, dw1lo, idesc1);
+          mma_ss_acc(d1, ax + (kStepX >> 4), dw1hi + (kStepW1 >> 4), idesc1);
+          mma_ss_acc(d1, axlo + (kStepX >> 4), dw1hi + (kStepW1 >> 4), idesc1);
+          mma_ss_acc(d1, ax + (kStepX >> 4), dw1lo + (kStepW1 >> 4), idesc1);
+          }
+          mma_commit(&sm.l1_done[b]);
+        } else {
+          mbar_arrive(&sm.l1_done[b]);                            // wakes E1, which then reads the stop word
+        }
+        PROF(1);
+        // ---- Linear-2 of tile t-1, chunk by chunk as E1 stages them -----------------------------------------------------------
+        if (t > 0) {
+          const uint32_t u = t - 1, j = u & 1u;
+          const uint32_t d1 = tmem + kColD1 + j * kN1;
+          const uint32_t d2 = tmem + kColD2 + j * (2 * kN2);
+          mbar_wait(&sm.d2_free[j], ((u >> 1) & 1u) ^ 1u, kWaitD2Free);     // E2 has read the previous use of D2[j]
+          PROF(2);
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c, ++g) {
+            const uint32_t s = g & 1u;
+            mbar_wait(&sm.a_full[s], (g >> 1) & 1u, kWaitAFull);
+            PROF(3);
+            fence_after();
+            const uint32_t a_lo = tmem + kColALo + s * kChunk;
+#pragma unroll
+            for (int ks = 0; ks < ((M6A_ABL & 4) ? 0 : kChunk / 8); ++ks) {
+              const int kstep = c * (kChunk / 8) + ks;
+              const uint64_t bw = dw2 + static_cast<uint64_t>(kstep) * (kStepW2 >> 4);
+              if (kstep == 0) mma_ts(d2, d1, bw, idesc64, 0u);             // [main | corr] = A_hi . [W2_hi ; W2_lo]^T
+              else mma_ts_acc(d2, d1 + kstep * 8, bw, idesc64);
+              mma_ts_acc(d2 + kN2, a_lo + ks * 8, bw, idesc32);            // corr += A_lo . W2_hi^T
+            }
+            mma_commit(&sm.a_free[s]);
+            PROF(4);
+          }
+          mma_commit(&sm.d2_full[j]);
+        }
+        if (stop) break;
+      }
+      PROF_STORE(10, true);
+    }
+  } else if (warp >= kE1Warp0 && warp < kE1Warp0 + kRoleWarps) {
+    // ======================================== E1: relu + hi/lo split of D1, chunk by chunk ================================
+    const int et = tid - kE1Warp0 * 32;                         // 0..255
+    const int half = et >> 7;                                   // which 16 columns of every 32-column chunk
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    uint32_t g = 0;
+    PROF_DECL;
+    for (uint32_t t = 0;; ++t) {
+      const uint32_t b = t & 1u;
+      // (not x_full: the staging warps may run two phases of it ahead of this role, and a parity wait cannot lag by two)
+      mbar_wait(&sm.l1_done[b], (t >> 1) & 1u, kWaitL1Done);
+      if (sm.x_ctrl[t % kCtrlRing] == 0) break;                  // the MMA issuer arrives on l1_done for the stop tile too
+      fence_after();
+      PROF(0);
+      const uint32_t d1 = tmem + kColD1 + b * kN1 + half * kHalfCols + lane_base;
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c, ++g) {
+        const uint32_t s = g & 1u;
+        uint32_t v[kHalfCols], l[kHalfCols];
+        if (!(M6A_ABL & 2)) {
+          tmem_ld16(d1 + c * kChunk, v);
+          wait_ld();
+        }
+        PROF(1);
+        if (!(M6A_ABL & 2)) {
+#pragma unroll
+          for (int i = 0; i < kHalfCols; ++i) {
+            const float h = fmaxf(__uint_as_float(v[i]), 0.0f);
+            const float hi = rn_tf32(h);
+            v[i] = __float_as_uint(hi);
+            l[i] = __float_as_uint(h - hi);
+          }
+        }
+        PROF(2);
+        mbar_wait(&sm.a_free[s], ((g >> 1) & 1u) ^ 1u, kWaitAFree);      // the MMAs of chunk g-2 have read this A_lo slot
+        fence_after();
+        PROF(3);
+        if (!(M6A_ABL & 2)) {
+          tmem_st16(d1 + c * kChunk, v);                                              // A_hi of Linear-2, in place
+          tmem_st16(tmem + kColALo + s * kChunk + half * kHalfCols + lane_base, l);   // A_lo
+          wait_st();
+        }
+        fence_before();
+        mbar_arrive(&sm.a_full[s]);
+        PROF(4);
+      }
+    }
+    PROF_STORE(30, et == 0);
+  } else if (warp >= kSeWarp0 && warp < kSeWarp0 + kRoleWarps) {
+    // ======================================== staging of X + E2 (sigmoid, outputs) =========================================
+    const int et = tid - kSeWarp0 * 32;                         // 0..255
+    const int row = et & (kTileM - 1);                          // row of the tile = TMEM lane
+    const int half = et >> 7;                                   // which 8 inputs / which 16 outputs
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int emb_dim = image->emb_dim, n_kmer = image->n_kmer;
+    unsigned long long* tile_counter =
+        reinterpret_cast<unsigned long long*>(const_cast<long long*>(a.tile_bounds)) + a.n_tiles + 1;
+
+    // ---- slab / tile generator (uniform over the 256 threads of this role) -----------------------------------------------
+    long long tile_s1 = 0, s0 = 0, r0 = 0, s_next = 0;
+    int ns = 0, nr = 0, base = 0, slot = -1;
+    uint32_t n_slabs = 0;               // slabs started by this CTA (slot = n % kSlots)
+    bool exhausted = false, have_tile = false;
+
+    auto open_slab = [&](bool stop_marker) {
+      slot = static_cast<int>(n_slabs % kSlots);
+      mbar_wait(&sm.slab_empty[slot], ((n_slabs / kSlots) & 1u) ^ 1u, kWaitSlabEmpty);
+      ++n_slabs;
+      if (stop_marker) {
+        if (et == 0) sm.meta[slot].stop = 1;
+        return;
+      }
+      if (et <= ns) sm.roff[slot][et] = static_cast<int>(a.read_off[s0 + et] - r0);
+      if (et < ns) {
+        sm.cnt[slot][et] = 0;
+#pragma unroll
+        for (int t = 0; t < kKmerPos; ++t) {
+          int k = a.kmer_idx != nullptr ? a.kmer_idx[(s0 + et) * kKmerPos + t] : 0;
+          sm.kid[slot][et][t] = min(max(k, 0), n_kmer - 1);
+        }
+      }
+      if (et == 0) {
+        SlabMeta m;
+        m.s0 = s0; m.r0 = r0; m.ns = ns; m.nr = nr; m.stop = 0; m.pad = 0;
+        sm.meta[slot] = m;
+      }
+      named_bar_sync(kBarSe, kRoleThreads);
+    };
+
+    // next MMA tile (advances slices / tiles as needed); slabs without rows are handed to the MC warps directly
+    auto next_tile = [&]() -> TileInfo {
+      TileInfo ti;
+      ti.exists = false; ti.valid = false; ti.last = false; ti.grow = 0; ti.slot = 0; ti.lr = 0; ti.site_l = 0;
+      while (!exhausted && base >= nr) {                          // current slab exhausted (initially nr = 0)
+        if (!have_tile || s_next >= tile_s1) {                    // next tile of the dynamic counter
+          named_bar_sync(kBarSe, kRoleThreads);                   // everyone has consumed the previous broadcast
+          if (et == 0) sm.next_tile = static_cast<long long>(atomicAdd(tile_counter, 1ull));
+          named_bar_sync(kBarSe, kRoleThreads);
+          const long long tile = sm.next_tile;
+          if (tile >= a.n_tiles) {
+            exhausted = true;
+            break;
+          }
+          s_next = a.tile_bounds[tile];
+          tile_s1 = a.tile_bounds[tile + 1];
+          have_tile = true;
+          if (s_next >= tile_s1) continue;                        // a tile without sites
+        }
+        s0 = s_next;
+        ns = static_cast<int>(min(static_cast<long long>(kSlabSites), tile_s1 - s0));
+        s_next = s0 + ns;
+        r0 = a.read_off[s0];
+        nr = static_cast<int>(a.read_off[s0 + ns] - r0);
+        base = 0;
+        open_slab(false);
+        if (nr == 0 && half == 0) mbar_arrive(&sm.slab_full[slot]);   // nothing to encode: sites without reads (NaN)
+      }
+      if (exhausted) return ti;
+      ti.exists = true;
+      ti.slot = slot;
+      ti.lr = base + row;
+      ti.valid = ti.lr < nr;
+      ti.grow = r0 + ti.lr;
+      base += kTileM;
+      ti.last = base >= nr;
+      if (ti.valid) {
+        int lo = 0, hi = ns;                                       // site of the row: last s with roff[s] <= lr
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (sm.roff[slot][mid] <= ti.lr) lo = mid; else hi = mid;
+        }
+        ti.site_l = lo;
+      }
+      return ti;
+    };
+
+    // asynchronous prefetch of this thread's 8 inputs of tile `ti` into fbuf[pb][row][8 * half ..] (no register round trip)
+    auto prefetch_inputs = [&](const TileInfo& ti, uint32_t pb) {
+      float* dst = &sm.fbuf[pb][row][8 * half];
+      if (ti.exists && ti.valid) {
+        const float* xr = a.feats + ti.grow * kNSig;
+        if (half == 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cp_async4(dst + k, xr + k);
+        } else {
+          cp_async4(dst, xr + 8);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) dst[1 + k] = 0.0f;
+          if (emb_dim == 2) {
+#pragma unroll
+            for (int t = 0; t < kKmerPos; ++t) {
+              const float* e = image->emb + 2 * sm.kid[ti.slot][ti.site_l][t];
+              cp_async4(dst + 1 + 2 * t, e);
+              cp_async4(dst + 2 + 2 * t, e + 1);
+            }
+          } else if (emb_dim == 1) {
+#pragma unroll
+            for (int t = 0; t < kKmerPos; ++t) cp_async4(dst + 1 + t, image->emb + sm.kid[ti.slot][ti.site_l][t]);
+          }
+          dst[7] = 1.0f;                                         // bias column
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[k] = 0.0f;
+      }
+      cp_async_commit();
+    };
+    // this thread's 8 inputs of the prefetched tile -> RN_tf32 split -> its two k-chunks of X[b]
+    auto stage_x = [&](uint32_t b, uint32_t pb) {
+      cp_async_wait_all();
+      const float4* src = reinterpret_cast<const float4*>(&sm.fbuf[pb][row][8 * half]);
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const float4 f = src[jj];
+        const float4 h = make_float4(rn_tf32(f.x), rn_tf32(f.y), rn_tf32(f.z), rn_tf32(f.w));
+        const float4 l = make_float4(f.x - h.x, f.y - h.y, f.z - h.z, f.w - h.w);
+        *reinterpret_cast<float4*>(sm.x[b][0][2 * half + jj][row]) = h;
+        *reinterpret_cast<float4*>(sm.x[b][1][2 * half + jj][row]) = l;     // the hardware truncates lo to TF32
+      }
+    };
+
+    // Per iteration t: stage X(t) | prefetch the inputs of tile t+1 | E2 of tile t-2 (its Linear-2 has had two tiles of time).
+    TileInfo ti_s = next_tile();          // tile staged in this iteration
+    TileInfo ti_1, ti_2;                  // tiles t-1, t-2
+    ti_1.exists = false;
+    ti_2.exists = false;
+    prefetch_inputs(ti_s, 0);
+    bool stop_sent = false;
+    PROF_DECL;
+    for (uint32_t t = 0;; ++t) {
+      const uint32_t b = t & 1u;
+      // ---- (1) stage X(t) (or publish the stop) ---------------------------------------------------------------------------
+      TileInfo ti_n;
+      ti_n.exists = false;
+      if (!stop_sent) {
+        if (ti_s.exists) {
+          if (t >= 2) mbar_wait(&sm.l1_done[b], ((t - 2) >> 1) & 1u, kWaitL1DoneSe);   // Linear-1 of tile t-2 has consumed X[b]
+          PROF(0);
+          cp_async_wait_all();
+          PROF(1);
+          if (!(M6A_ABL & 16)) stage_x(b, b);
+          if (et == 0) sm.x_ctrl[t % kCtrlRing] = 1;
+          PROF(2);
+          if (!(M6A_ABL & 1)) fence_proxy_async();
+          PROF(3);
+        } else {
+          if (et == 0) sm.x_ctrl[t % kCtrlRing] = 0;
+          stop_sent = true;
+        }
+        mbar_arrive(&sm.x_full[b]);
+        PROF(4);
+        // ---- (2) the inputs of tile t+1 travel to shared memory meanwhile ----------------------------------------------
+        if (ti_s.exists) {
+          ti_n = next_tile();
+          PROF(5);
+          if (!(M6A_ABL & 16)) prefetch_inputs(ti_n, b ^ 1u);
+        }
+        PROF(6);
+      }
+      // ---- (3) E2 of tile t-2: this warp's 16 outputs; the first half finishes the row ------------------------------------
+      if (ti_2.exists) {
+        const uint32_t u = t - 2, j = u & 1u;
+        const uint32_t d2 = tmem + kColD2 + j * (2 * kN2) + half * kHalfCols + lane_base;
+        mbar_wait(&sm.d2_full[j], (u >> 1) & 1u, kWaitD2Full);
+        fence_after();
+        PROF(7);
+        uint32_t vm[kHalfCols], vc[kHalfCols];
+        if (!(M6A_ABL & 8)) {
+          tmem_ld16(d2, vm);
+          tmem_ld16(d2 + kN2, vc);
+          wait_ld();
+        }
+        fence_before();
+        mbar_arrive(&sm.d2_free[j]);
+        float z = 0.0f;
+#pragma unroll
+        for (int k = 0; k < ((M6A_ABL & 8) ? 0 : kHalfCols); ++k) {
+          const int o = half * kHalfCols + k;
+          const float h2 = (__uint_as_float(vm[k]) + __uint_as_float(vc[k])) + sm.b2[o];
+          z = fmaf(sm.w3[o], fmaxf(h2, 0.0f), z);
+        }
+        if (half == 1) sm.zpart[j][row] = z;
+        named_bar_sync(kBarSe, kRoleThreads);
+        PROF(8);
+        if (half == 0) {
+          z = (z + sm.zpart[j][row]) + sm.b3;
+          const float p = 1.0f / (1.0f + expf(-z));
+          if (ti_2.valid) {
+            a.read_prob[ti_2.grow] = p;
+            if (ti_2.lr < kQCap) sm.q[ti_2.slot][ti_2.lr] = 1.0f - p;
+            if (p >= a.read_threshold) atomicAdd(&sm.cnt[ti_2.slot][ti_2.site_l], 1);
+          }
+          if (ti_2.last) mbar_arrive(&sm.slab_full[ti_2.slot]);
+        }
+        PROF(9);
+      }
+      // ---- (4) rotate -------------------------------------------------------------------------------------------------------
+      ti_2 = ti_1;
+      ti_1 = ti_s;
+      ti_s = ti_n;
+      if (stop_sent && !ti_1.exists && !ti_2.exists) break;
+    }
+    PROF_STORE(0, et == 0);
+    // tell the MC warps that no slab follows
+    open_slab(true);
+    if (half == 0) mbar_arrive(&sm.slab_full[slot]);
+  } else {
+    // ======================================== Monte-Carlo pooling ============================================================
+    const int mcw = warp == 0 ? 0 : (warp < 4 ? warp - 1 : warp - 17);     // 0, 2, 3, 20..31 -> 0..14
+    const int mct = mcw * 32 + lane;
+    const float n_iters_f = static_cast<float>(a.n_iters);
+    PROF_DECL;
+    for (uint32_t n = 0;; ++n) {
+      const int slot = static_cast<int>(n % kSlots);
+      mbar_wait(&sm.slab_full[slot], (n / kSlots) & 1u, kWaitSlabFull);
+      PROF(0);
+      const SlabMeta m = sm.meta[slot];
+      if (m.stop) break;
+      const int ns = m.ns;
+      const bool q_in_smem = m.nr <= kQCap;
+      const int* roff = sm.roff[slot];
+      const float* q = sm.q[slot];
+      float* partial = partial_base + static_cast<size_t>(slot) * kSlabSites * n_blocks;
+
+      const int items = ns * n_blocks;
+      auto lane_rounds = [&](int blk_) {
+        const long long it0 = static_cast<long long>(blk_) * ipl * 32 + lane;
+        const long long left = (static_cast<long long>(a.n_iters) - it0 + 31) / 32;
+        return static_cast<int>(left < 0 ? 0 : (left > ipl ? ipl : left));
+      };
+      auto run_single = [&](int item) {
+        const int sl_ = item / n_blocks, blk_ = item - sl_ * n_blocks;
+        const int nreads = roff[sl_ + 1] - roff[sl_];
+        float v = 0.0f;
+        if (nreads > 0) {
+          const int rounds = lane_rounds(blk_);
+          Mwc64x gen;
+          gen.seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk_),
+                   static_cast<unsigned long long>(a.site_id_base + m.s0 + sl_), a.seed);
+          if (q_in_smem) {
+            v = mc_lane_smem<NS>(q + roff[sl_], static_cast<uint32_t>(nreads), gen, rounds);
+          } else {
+            v = mc_lane_generic(a.read_prob + m.r0 + roff[sl_], true, static_cast<uint32_t>(nreads), gen, rounds, NS, nullptr, 0);
+          }
+        }
+        v = warp_butterfly_sum(v);
+        if (lane == 0) partial[sl_ * n_blocks + blk_] = v;
+      };
+      // items (site, block) are dealt round-robin to the warps, kMcChains at a time (interleaved chains)
+      for (int item0 = mcw; item0 < ((M6A_ABL & 32) ? 0 : items); item0 += kMcChains * kMcWarps) {
+        int it[kMcChains], sl[kMcChains], blk[kMcChains], nn[kMcChains];
+        bool all = q_in_smem, paired = false;
+#pragma unroll
+        for (int i = 0; i < kMcChains; ++i) {
+          it[i] = item0 + i * kMcWarps;
+          const bool have = it[i] < items;
+          sl[i] = have ? it[i] / n_blocks : 0;
+          blk[i] = have ? it[i] - sl[i] * n_blocks : 0;
+          nn[i] = have ? roff[sl[i] + 1] - roff[sl[i]] : 0;
+          all = all && have && nn[i] > 0;
+          const bool pr = nn[i] <= static_cast<int>(kPairedMaxReads);
+          if (i == 0) paired = pr;
+          all = all && (pr == paired);
+        }
+        if (all) {          // warp-uniform
+          uint32_t qa[kMcChains], nu[kMcChains];
+          Mwc64x gen[kMcChains];
+          int rounds[kMcChains];
+          float v[kMcChains];
+#pragma unroll
+          for (int i = 0; i < kMcChains; ++i) {
+            qa[i] = mc_smem_u32(q + roff[sl[i]]);
+            nu[i] = static_cast<uint32_t>(nn[i]);
+            rounds[i] = lane_rounds(blk[i]);
+            gen[i].seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk[i]),
+                        static_cast<unsigned long long>(a.site_id_base + m.s0 + sl[i]), a.seed);
+            v[i] = 0.0f;
+          }
+          if (paired) mc_rounds_xn<NS, true, kMcChains>(qa, nu, gen, rounds, v);
+          else mc_rounds_xn<NS, false, kMcChains>(qa, nu, gen, rounds, v);
+#pragma unroll
+          for (int i = 0; i < kMcChains; ++i) {
+            const float w = warp_butterfly_sum(v[i]);
+            if (lane == 0) partial[sl[i] * n_blocks + blk[i]] = w;
+          }
+        } else {
+#pragma unroll 1
+          for (int item = item0; item < items && item < item0 + kMcChains * kMcWarps; item += kMcWarps) run_single(item);
+        }
+      }
+      PROF(1);
+      named_bar_sync(kBarMc, kMcThreads);
+      PROF(2);
+      if (mct < ns) {
+        const int nreads = roff[mct + 1] - roff[mct];
+        float s = 0.0f;
+        for (int k = 0; k < n_blocks; ++k) s += partial[mct * n_blocks + k];
+        const size_t o = static_cast<size_t>(m.s0 + mct) * a.site_stride;
+        a.site_prob[o] = nreads > 0 ? s / n_iters_f : __int_as_float(0x7fc00000);
+        a.mod_count[o] = sm.cnt[slot][mct];
+      }
+      named_bar_sync(kBarMc, kMcThreads);
+      if (mct == 0) mbar_arrive(&sm.slab_empty[slot]);
+      PROF(3);
+    }
+    PROF_STORE(20, mct == 0);
+  }
+
+  // ---- teardown -----------------------------------------------------------------------------------------------------------
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, kTmemCols);
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------------
+static bool g_tc_attr_done[64];
+static int g_tc_smem_set[64];
+
+cudaError_t set_trap_record(int* mapped_device_ptr) {
+  return cudaMemcpyToSymbol(m6a::tc::g_trap_record, &mapped_device_ptr, sizeof(int*));
+}
+
+}  // namespace tcx
+
+cudaError_t launch_mil_infer_tc(const KernelArgs& a, const tcx::WeightImageTc* d_image, int n_sms, cudaStream_t stream,
+                                LaunchInfo* info) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  const int smem = static_cast<int>(tcx::tc_smem_bytes(a.n_blocks));
+  auto kern = tcx::mil_infer_tc_kernel<20>;
+  if (!tcx::g_tc_attr_done[dev] || tcx::g_tc_smem_set[dev] < smem) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    tcx::g_tc_attr_done[dev] = true;
+    tcx::g_tc_smem_set[dev] = smem;
+  }
+  long long grid = n_sms;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid < 1) grid = 1;
+  if (info) {
+    info->grid = static_cast<int>(grid);
+    info->block = tcx::kTcThreads;
+    info->smem_bytes = smem;
+    info->tile_reads = a.tile_reads;
+  }
+  kern<<<static_cast<unsigned>(grid), tcx::kTcThreads, smem, stream>>>(a, d_image);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_set_trap_record(int* mapped_device_ptr) { return tcx::set_trap_record(mapped_device_ptr); }
+
+cudaError_t tc_read_profile(unsigned long long* out32) {
+#if M6A_TC_PROFILE
+  return cudaMemcpyFromSymbol(out32, tcx::g_prof, 40 * sizeof(unsigned long long));
+#else
+  for (int i = 0; i < 40; ++i) out32[i] = 0;
+  return cudaSuccess;
+#endif
+}
+
+}  // namespace m6a

@@ -48,4 +48,43 @@ struct DeviceModel {
   int32_t emb_dim;
 };
 
+
+// ---- tensor-core read encoder (m6a_kernel_tc.cu): tcgen05 kind::tf32, error-compensated 3xTF32 products ------------------
+// Both Linear blocks run on the 5th-generation tensor cores, one tile of 128 reads (TMEM lanes) at a time:
+//   Linear-1  D1[128 x 160] = [x(9) | emb(6) | 1] (K = 16) . W1a^T, W1a = [w1 | b1] (BatchNorm folded)
+//   Linear-2  D2[128 x 32]  = relu(D1) (K = 160, A operand read from TMEM) . W2^T
+// A 32-bit operand is truncated to TF32 by the hardware (measured, profiles/r02_tcgen05_probe.log), so every operand v is
+// split into hi = RN_tf32(v) (stored with the low 13 mantissa bits zero) and lo = v - hi, and
+//   A.B ~= A_hi.B_hi + (A_lo.B_hi + A_hi.B_lo)
+// The tensor core adds into its float32 accumulator with truncation (a CPU model of exactly that reproduces the measured
+// errors of round 1's experimental kernel to 10 %), so Linear-2 keeps the two small terms in their OWN accumulator and the
+// epilogue adds main + correction once in round-to-nearest float32.
+namespace tcx {
+constexpr int kTileM = 128;        // reads per MMA tile (TMEM lanes, UMMA M)
+constexpr int kK1 = 16;            // Linear-1 inputs: 9 signal | 3 x emb_dim (<= 6) | bias column
+constexpr int kN1 = 160;           // hidden units, padded from <= 152 to 5 chunks of 32
+constexpr int kN2 = kH2;           // 32
+constexpr int kChunk = 32;         // hidden units per relu/split chunk = 4 K-steps of Linear-2
+constexpr int kChunks = kN1 / kChunk;
+constexpr int kEmbMax = 4096 * 2;  // embedding table floats kept in the image (n_kmer * emb_dim)
+
+// Weights as the kernel's shared memory holds them: K-major no-swizzle UMMA operands [k-chunk of 4][row][4].
+//   w1hi/w1lo  rows = hidden units, columns = [9 signal | 3 x emb | 0.. | b1 at 15]
+//   w2s        rows 0..31 = W2_hi, rows 32..63 = W2_lo: one N = 64 MMA computes A_hi.W2_hi (main accumulator columns) and
+//              A_hi.W2_lo (correction columns) at once; A_lo.W2_hi is an N = 32 MMA on rows 0..31 of the same operand
+struct alignas(16) WeightImageTc {
+  float w1hi[kK1 / 4][kN1][4];
+  float w1lo[kK1 / 4][kN1][4];
+  float w2s[kN1 / 4][2 * kN2][4];
+  float b2[kN2];
+  float w3[kN2];
+  float b3;
+  int32_t emb_dim;
+  int32_t n_kmer;
+  int32_t pad;
+  float emb[kEmbMax];              // read from global memory (L1/L2 resident)
+};
+constexpr int kTcOperandBytes = (2 * kK1 * kN1 + kN1 * 2 * kN2) * 4;   // w1hi | w1lo | w2s, copied to shared memory
+}  // namespace tcx
+
 }  // namespace m6a

@@ -101,6 +101,36 @@ __device__ __forceinline__ void mc_lane_smem_x2(const float* qsa, uint32_t na, M
   }
 }
 
+// NC (site, block) items of the same index regime at once, chains interleaved instruction by instruction (the tensor-core
+// kernel has fewer Monte-Carlo warps than the CUDA-core kernel and hides the serial MWC latency inside each warp instead).
+// Identical results to NC mc_lane_smem calls: every chain accumulates its own rounds in round order.
+template <int NS, bool PAIRED, int NC>
+__device__ __forceinline__ void mc_rounds_xn(const uint32_t (&qa)[NC], const uint32_t (&n)[NC], Mwc64x (&g)[NC],
+                                             const int (&rounds)[NC], float (&v)[NC]) {
+  constexpr int kSteps = PAIRED ? NS / 2 : NS;
+  int kc = rounds[0];
+#pragma unroll
+  for (int i = 1; i < NC; ++i) kc = min(kc, rounds[i]);
+  for (int k = 0; k < kc; ++k) {
+    float p[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) p[i] = 1.0f;
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) mc_step<PAIRED>(qa[i], n[i], g[i], p[i]);
+    }
+    if (PAIRED && (NS & 1)) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) mc_step<PAIRED>(qa[i], n[i], g[i], p[i], false);
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] += 1.0f - p[i];
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) mc_rounds<NS, PAIRED>(qa[i], n[i], g[i], kc, rounds[i], v[i]);   // ragged tails
+}
+
 // generic path: any n_samples, q from shared memory or 1 - read_prob from global, optional explicit indices
 __device__ __forceinline__ float mc_lane_generic(const float* qbase, bool from_prob, uint32_t n, Mwc64x& g, int rounds,
                                                  int ns, const uint16_t* __restrict__ explicit_idx,

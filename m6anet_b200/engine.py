@@ -62,6 +62,22 @@ class MilEngine:
     def device(self):
         return self._torch.device("cuda", self.device_index)
 
+    def set_encoder(self, encoder: str):
+        """'tc' (tcgen05 tensor-core read encoder, the default) or 'ffma' (CUDA-core FFMA2 encoder)."""
+        if encoder not in _cabi.ENCODERS:
+            raise ValueError(f"unknown encoder {encoder!r}; one of {sorted(_cabi.ENCODERS)}")
+        _cabi.check(self._lib.m6a_model_set_encoder(self._handle, _cabi.ENCODERS[encoder]), "m6a_model_set_encoder")
+
+    @property
+    def encoder(self) -> str:
+        return "tc" if self._lib.m6a_model_get_encoder(self._handle) == 1 else "ffma"
+
+    def trap_record(self):
+        """Arms (first call) / reads the debug record of the tensor-core kernel's bounded waits: [site, block, thread, parity]."""
+        out = (C.c_int32 * 4)()
+        _cabi.check(self._lib.m6a_debug_trap_record(self._handle, out), "m6a_debug_trap_record")
+        return list(out)
+
     def set_tile_reads(self, tile_reads: int = 0):
         """Feature rows per tile (64..4096); 0 = automatic (a multiple of the site depth near 1000 rows)."""
         _cabi.check(self._lib.m6a_model_set_tile_reads(self._handle, int(tile_reads)), "m6a_model_set_tile_reads")
@@ -125,6 +141,42 @@ class MilEngine:
                 st.cuda_stream)
         _cabi.check(rc, "m6a_mil_infer_f32")
         return read_prob, site_prob, mod_count
+
+    def infer_device_packed(self, feats, read_off, kmer_idx, n_iters: int, seed: int = 0, site_id_base: int = 0,
+                            n_samples: int = DEFAULT_N_SAMPLES, read_threshold: float = 0.033379376, read_prob=None,
+                            site_out=None, stream=None):
+        """m6a_mil_infer_packed_f32: like infer_device, but the kernel writes the two per-site outputs interleaved into
+        `site_out` [>= sites, 2] float32 words (site_prob, mod_count bits) -- the send buffer of the all-gather of a
+        multi-GPU run, so no pack kernels run.  Returns (read_prob, site_out)."""
+        torch = self._torch
+        n_sites = read_off.numel() - 1
+        total_reads = feats.shape[0]
+        if not (feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous() and feats.dim() == 2 and feats.shape[1] == 9):
+            raise ValueError("MilEngine.infer_device_packed: feats must be a contiguous float32 CUDA tensor [reads, 9]")
+        if not (read_off.is_cuda and read_off.dtype == torch.int64 and read_off.is_contiguous() and read_off.numel() >= 1):
+            raise ValueError("MilEngine.infer_device_packed: read_off must be a contiguous int64 CUDA tensor [sites + 1]")
+        if kmer_idx is not None and not (kmer_idx.is_cuda and kmer_idx.dtype == torch.int32 and kmer_idx.is_contiguous()
+                                         and kmer_idx.numel() == 3 * n_sites):
+            raise ValueError("MilEngine.infer_device_packed: kmer_idx must be a contiguous int32 CUDA tensor [sites, 3]")
+        if read_prob is None:
+            read_prob = torch.empty(total_reads, dtype=torch.float32, device=self.device)
+        if site_out is None:
+            site_out = torch.empty((n_sites, 2), dtype=torch.float32, device=self.device)
+        if not (site_out.is_cuda and site_out.dtype == torch.float32 and site_out.is_contiguous() and site_out.dim() == 2
+                and site_out.shape[1] == 2 and site_out.shape[0] >= n_sites and read_prob.numel() >= total_reads):
+            raise ValueError("MilEngine.infer_device_packed: site_out must be a contiguous float32 CUDA tensor [>= sites, 2]")
+        ws_bytes = int(self._lib.m6a_mil_workspace_bytes(total_reads))
+        workspace = torch.empty(ws_bytes // 8, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device) if stream is None else stream
+            if stream is not None:
+                workspace.record_stream(st)
+            rc = self._lib.m6a_mil_infer_packed_f32(
+                self._handle, feats.data_ptr(), read_off.data_ptr(), None if kmer_idx is None else kmer_idx.data_ptr(),
+                n_sites, total_reads, site_id_base, n_samples, n_iters, seed & 0xFFFFFFFFFFFFFFFF, read_threshold,
+                read_prob.data_ptr(), site_out.data_ptr(), workspace.data_ptr(), ws_bytes, st.cuda_stream)
+        _cabi.check(rc, "m6a_mil_infer_packed_f32")
+        return read_prob, site_out
 
     # ---- host-buffer call (m6a_mil_infer_host_f32): chunked H2D / kernel / D2H pipeline -------------
     def infer_host(self, feats: np.ndarray, read_off: np.ndarray, kmer_idx: Optional[np.ndarray], n_iters: int,

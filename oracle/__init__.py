@@ -21,6 +21,7 @@ from .philox import (philox4x32_10, sample_indices, sample_indices_many, sample_
 from .mil_oracle import (  # noqa: F401
     ReadEncoderParams,
     read_probabilities,
+    read_probabilities_float64,
     noisy_or_site_probability,
     mod_ratio,
     mil_inference,

@@ -76,6 +76,22 @@ def read_probabilities(params: ReadEncoderParams, feats: np.ndarray, kmer: Optio
     return p.astype(f32)
 
 
+
+def read_probabilities_float64(params: ReadEncoderParams, feats: np.ndarray, kmer: Optional[np.ndarray]) -> np.ndarray:
+    """The read encoder of `read_probabilities` evaluated in float64 (exact to ~1e-15): the yardstick for float32 error.
+    Over millions of reads every float32 evaluation -- the reference's own torch calls included -- sits up to ~1.9e-6
+    from this value, so full-size checks hold the kernel to it (3e-6) instead of to another float32 evaluation."""
+    f64 = np.float64
+    x = np.asarray(feats).astype(f64)
+    if params.emb is not None:
+        x = np.concatenate([x, params.emb.astype(f64)[np.asarray(kmer)].reshape(-1, 3 * params.emb.shape[1])], axis=1)
+    h = x @ params.w1.astype(f64).T + params.b1
+    h = (h - params.bn_mean) / np.sqrt(params.bn_var.astype(f64) + params.bn_eps) * params.bn_gamma + params.bn_beta
+    h = np.maximum(h, 0)
+    h = np.maximum(h @ params.w2.astype(f64).T + params.b2, 0)
+    z = h @ params.w3.astype(f64).reshape(-1) + float(params.b3.reshape(-1)[0])
+    return 1.0 / (1.0 + np.exp(-z))
+
 def noisy_or_site_probability(read_prob: np.ndarray, idx: np.ndarray) -> np.float32:
     """Monte-Carlo noisy-OR for ONE site on a given index stream.
 

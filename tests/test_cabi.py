@@ -82,8 +82,10 @@ def test_batchnorm_fold_matches_unfolded_oracle():
 
 
 def test_sass_shows_the_blackwell_native_paths():
-    """cuobjdump evidence (no GPU needed): TMA bulk copy + mbarrier for the feature tiles, packed FFMA2 fed from uniform
-    registers (weights as a __grid_constant__ parameter), quarter-rate wide multiplies only in the MC stream."""
+    """cuobjdump evidence (no GPU needed).  CUDA-core kernel: TMA bulk copy + mbarrier for the feature tiles, packed FFMA2 fed
+    from uniform registers (weights as a __grid_constant__ parameter), no tensor-core instruction.  Tensor-core kernel:
+    tcgen05.mma (UTCHMMA) with TMEM loads / stores (LDTM / STTM) and MMA-completion barriers (UTCBAR); never the legacy
+    mma.sync path (HMMA)."""
     import re
     import subprocess
     from m6anet_b200 import _cabi
@@ -91,8 +93,11 @@ def test_sass_shows_the_blackwell_native_paths():
     assert "UBLKCP" in sass and "SYNCS" in sass                       # cp.async.bulk + mbarrier transaction count
     assert re.search(r"FFMA2 .*UR\d+\.F32x2", sass)                    # uniform-register pair operand
     assert re.search(r"LDCU\.64 UR\d+, c\[0x0\]\[UR\d+", sass)          # weights streamed from the parameter bank
-    assert "HMMA" not in sass and "UTCHMMA" not in sass               # no tensor cores on this path (north_star)
-    assert "LDL" not in sass.split("mil_infer_kernelILi20")[1].split("Function :")[0]   # no spills in the headline kernel
+    ffma = sass.split("mil_infer_kernelILi20")[1].split("Function :")[0]
+    assert "UTCHMMA" not in ffma and "LDL" not in ffma                 # CUDA-core kernel: no tensor cores, no spills
+    tc = sass.split("mil_infer_tc_kernelILi20")[1].split("Function :")[0]
+    assert tc.count("UTCHMMA") >= 14 and "LDTM" in tc and "STTM" in tc and "UTCBAR" in tc and "LDGSTS" in tc
+    assert not re.search(r"\bHMMA\b", sass)                            # no legacy mma.sync anywhere
 
 
 def test_auto_tile_reads_policy(lib):

@@ -253,18 +253,7 @@ def test_invalid_arguments_are_rejected(synthetic_inputs):
     torch.cuda.synchronize()
 
 
-def _read_probs_float64(params, feats, kmer_rows):
-    """The read encoder of oracle.read_probabilities evaluated in float64 (exact to ~1e-15): the yardstick for float32 error."""
-    f64 = np.float64
-    x = feats.astype(f64)
-    if params.emb is not None:
-        x = np.concatenate([x, params.emb.astype(f64)[kmer_rows].reshape(-1, 3 * params.emb.shape[1])], axis=1)
-    h = x @ params.w1.astype(f64).T + params.b1
-    h = (h - params.bn_mean) / np.sqrt(params.bn_var.astype(f64) + params.bn_eps) * params.bn_gamma + params.bn_beta
-    h = np.maximum(h, 0)
-    h = np.maximum(h @ params.w2.astype(f64).T + params.b2, 0)
-    z = h @ params.w3.astype(f64).reshape(-1) + float(params.b3.reshape(-1)[0])
-    return 1.0 / (1.0 + np.exp(-z))
+from oracle import read_probabilities_float64 as _read_probs_float64   # noqa: E402
 
 
 def _full_size_check(tag, n_sites, n_reads, thr, seed=0, site_id_base=0, pooled_from=1):

@@ -1,12 +1,12 @@
 // Bring-up probe for the tcgen05 building blocks of the EXPERIMENTAL tensor-core encoder
-// (m6anet_b200/csrc/experimental/m6a_tc_device.cuh).  One CTA of 128 threads, every step checked against the host:
+// (m6anet_b200/csrc/m6a_tc.cuh).  One CTA of 128 threads, every step checked against the host:
 //   1. TMEM alloc / tcgen05.st / tcgen05.ld round trip (lane quadrants, column addressing)
 //   2. one tcgen05.mma kind::tf32 SS (A, B from shared memory, K-major SWIZZLE_NONE descriptors), M128 x N x K8
 //   3. the same product with A from TMEM (TS)
 //   4. accumulation over two K-steps (descriptor advance by kStep), N = 160 and N = 32
 //   5. what the tensor core does with the low 13 mantissa bits of a 32-bit operand (truncate / round / use them)
 // Inputs are small integers (exact in TF32), so every expected value is exact.  Every mbarrier wait is bounded.
-//   nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I m6anet_b200/csrc/experimental \
+//   nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I m6anet_b200/csrc \
 //        -o tools/microbench/tcgen05_probe tools/microbench/tcgen05_probe.cu && timeout 60 tools/microbench/tcgen05_probe
 #include <cuda_runtime.h>
 
@@ -15,9 +15,19 @@
 #include <cstdlib>
 #include <vector>
 
-#include "m6a_tc_device.cuh"
+#include "m6a_tc.cuh"
 
 using namespace m6a::tc;
+#define tc_mbar_init mbar_init
+#define tc_fence_barrier_init fence_barrier_init
+#define tc_fence_proxy_async fence_proxy_async
+#define tc_fence_before fence_before
+#define tc_fence_after fence_after
+#define tc_wait_st wait_st
+#define tc_wait_ld wait_ld
+#define tc_commit mma_commit
+#define tc_smem_u32 smem_u32
+#define tc_mbar_wait(b, p) mbar_wait(b, p, 99)
 
 constexpr int kRows = 128;
 constexpr int kNMax = 160;
