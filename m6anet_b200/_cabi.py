@@ -192,3 +192,42 @@ def pinned_empty(shape, dtype) -> "_np.ndarray":
     buf = (C.c_char * n_bytes).from_address(p.value)
     buf._owner = owner                                    # the ctypes buffer is the base object of the array
     return _np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+class PinnedPool:
+    """Recycles page-locked blocks (cudaHostAlloc costs milliseconds per call): `empty` hands out an array backed by a free
+    block of at least the requested size, `give_back` returns the block of an array obtained from this pool."""
+
+    def __init__(self):
+        import threading
+        self._free = []          # (n_bytes, uint8 array)
+        self._lent = {}          # data pointer -> uint8 block
+        self._lock = threading.Lock()     # ingest, GPU and emit threads share one pool
+
+    def empty(self, shape, dtype):
+        dtype = _np.dtype(dtype)
+        shape = (shape,) if isinstance(shape, (int, _np.integer)) else tuple(int(x) for x in shape)
+        n_bytes = int(_np.prod(shape, dtype=_np.int64)) * dtype.itemsize
+        if n_bytes == 0:
+            return _np.empty(shape, dtype=dtype)
+        with self._lock:
+            best = None
+            for i, (cap, _) in enumerate(self._free):
+                if cap >= n_bytes and (best is None or cap < self._free[best][0]):
+                    best = i
+            block = None if best is None else self._free.pop(best)[1]
+        if block is None:
+            block = pinned_empty(n_bytes + n_bytes // 4 + 4096, _np.uint8)
+        out = block[:n_bytes].view(dtype).reshape(shape)
+        with self._lock:
+            self._lent[out.ctypes.data] = block
+        return out
+
+    def give_back(self, *arrays):
+        for a in arrays:
+            if a is None or not hasattr(a, "ctypes") or a.size == 0:
+                continue
+            with self._lock:
+                block = self._lent.pop(a.ctypes.data, None)
+                if block is not None:
+                    self._free.append((block.nbytes, block))

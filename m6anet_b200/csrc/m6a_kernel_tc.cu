@@ -35,20 +35,33 @@ namespace tcx {
 using namespace m6a::tc;
 
 constexpr int kTcThreads = 1024;
+#ifndef M6A_TC_LAYOUT
+#define M6A_TC_LAYOUT 1     // 1: the latency-critical roles sit on the highest warp ids (12.73 vs 12.84 ms on the headline job)
+#endif
+#if M6A_TC_LAYOUT == 0
 constexpr int kMmaWarp = 1;
 constexpr int kE1Warp0 = 4;                  // warps 4..11 : E1 (relu / split), two per TMEM lane quadrant (quadrant = warp % 4)
 constexpr int kSeWarp0 = 12;                 // warps 12..19: staging of X + E2 (sigmoid, outputs), two per quadrant
+#else                                        // the latency-critical roles on the highest warp ids (scheduler priority experiment)
+constexpr int kMmaWarp = 31;
+constexpr int kE1Warp0 = 20;
+constexpr int kSeWarp0 = 12;
+#endif
 constexpr int kRoleWarps = 8;
 constexpr int kRoleThreads = kRoleWarps * 32;   // 256
 constexpr int kMcWarps = 15;                 // warps 0, 2, 3, 20..31
-constexpr int kMcThreads = kMcWarps * 32;
-constexpr int kMcChains = 4;                 // (site, block) items a Monte-Carlo warp interleaves
-constexpr int kSlots = 3;                    // slab slots in shared memory (q table, offsets, counters, partial sums)
+#ifndef M6A_MC_CHAINS
+#define M6A_MC_CHAINS 2     // measured on B200 (1 M x 50 x 1000): 2 chains 12.84 ms, 4 chains 13.34 ms
+#endif
+constexpr int kMcChains = M6A_MC_CHAINS;     // blocks of a site a Monte-Carlo warp interleaves
+constexpr int kSlots = 3;                    // slab slots in shared memory (q table, offsets, counters)
 constexpr int kSlabSites = kSitesPerTileMax; // 64
 constexpr int kTmemCols = 512;
 constexpr uint32_t kColD1 = 0, kColALo = 2 * kN1, kColD2 = 2 * kN1 + 2 * kChunk;   // 0 | 320 | 384
-static_assert(kColD2 + 2 * 2 * kN2 == kTmemCols, "TMEM column budget");
-constexpr int kBarSe = 1, kBarMc = 2;        // named barriers
+constexpr int kGroups = 2;                   // Linear-2 accumulator groups (chunks 0..2 | 3..4), each [main 32 | corr 32]
+constexpr int kGroup1Chunk = 3;              // first chunk of the second group
+static_assert(kColD2 + kGroups * 2 * kN2 == kTmemCols, "TMEM column budget");
+constexpr int kBarSe = 1;                    // named barrier of the staging / E2 role
 constexpr int kHalfCols = kChunk / 2;        // columns of a chunk per warp
 constexpr int kCtrlRing = 8;                 // per-tile control words (the staging warps run at most 4 tiles ahead of E1)
 
@@ -88,20 +101,18 @@ struct alignas(128) TcSmem {
   alignas(8) unsigned long long l1_done[2];     // MMA commit    -> E1, staging : D1[b] ready / X[b] consumed
   alignas(8) unsigned long long a_full[2];      // E1 (256)      -> MMA : chunk staged in D1 (hi) / A_lo slot
   alignas(8) unsigned long long a_free[2];      // MMA commit    -> E1 : A_lo slot consumed
-  alignas(8) unsigned long long d2_full[2];     // MMA commit    -> E2 : D2[j] complete
-  alignas(8) unsigned long long d2_free[2];     // E2 (256)      -> MMA : D2[j] read out
+  alignas(8) unsigned long long d2_full[1];     // MMA commit    -> E2 : D2 complete (both accumulator groups)
+  alignas(8) unsigned long long d2_free[1];     // E2 (256)      -> MMA : D2 read out
+  int done[kSlots];                             // MC warps finished with the slab of a slot
   alignas(8) unsigned long long slab_full[kSlots];   // E2 (128) -> MC
   alignas(8) unsigned long long slab_empty[kSlots];  // MC (1)   -> staging
-  // float partial[kSlots][kSlabSites][n_blocks] follows (dynamic)
 };
 static_assert(offsetof(TcSmem, w1lo) % 128 == 0 && offsetof(TcSmem, w2s) % 128 == 0 && offsetof(TcSmem, x) % 128 == 0,
               "UMMA operands must start on a 128-byte core-matrix boundary");
 static_assert(offsetof(TcSmem, w1hi) == 0 && offsetof(TcSmem, w2s) + sizeof(float) * kN1 / 4 * 2 * kN2 * 4 == kTcOperandBytes,
               "operand block is one contiguous copy of the image head");
 
-size_t tc_smem_bytes(int n_blocks) {
-  return sizeof(TcSmem) + static_cast<size_t>(kSlots) * kSlabSites * n_blocks * sizeof(float);
-}
+size_t tc_smem_bytes(int /*n_blocks*/) { return sizeof(TcSmem); }
 
 // ---- optional phase profile (-DM6A_TC_PROFILE=1): cycles per phase of one thread per role of block 0 ------------------------
 #ifndef M6A_TC_PROFILE
@@ -146,7 +157,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
-  float* partial_base = reinterpret_cast<float*>(smem_raw + sizeof(TcSmem));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_blocks = a.n_blocks, ipl = a.iters_per_lane;
 
@@ -166,12 +176,13 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
         mbar_init(&sm.l1_done[i], 1);
         mbar_init(&sm.a_full[i], kRoleThreads);
         mbar_init(&sm.a_free[i], 1);
-        mbar_init(&sm.d2_full[i], 1);
-        mbar_init(&sm.d2_free[i], kRoleThreads);
       }
+      mbar_init(&sm.d2_full[0], 1);
+      mbar_init(&sm.d2_free[0], kRoleThreads);
       for (int i = 0; i < kSlots; ++i) {
         mbar_init(&sm.slab_full[i], kTileM);
         mbar_init(&sm.slab_empty[i], 1);
+        sm.done[i] = 0;
       }
       fence_barrier_init();
     }
@@ -224,8 +235,7 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
         if (t > 0) {
           const uint32_t u = t - 1, j = u & 1u;
           const uint32_t d1 = tmem + kColD1 + j * kN1;
-          const uint32_t d2 = tmem + kColD2 + j * (2 * kN2);
-          mbar_wait(&sm.d2_free[j], ((u >> 1) & 1u) ^ 1u, kWaitD2Free);     // E2 has read the previous use of D2[j]
+          mbar_wait(&sm.d2_free[0], (u & 1u) ^ 1u, kWaitD2Free);            // E2 has read D2 of tile u-1
           PROF(2);
 #pragma unroll
           for (int c = 0; c < kChunks; ++c, ++g) {
@@ -234,18 +244,20 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
             PROF(3);
             fence_after();
             const uint32_t a_lo = tmem + kColALo + s * kChunk;
+            // two accumulator groups (K-steps of chunks 0..2 | 3..4): fewer truncating accumulations per accumulator
+            const uint32_t d2 = tmem + kColD2 + (c >= kGroup1Chunk ? 2 * kN2 : 0);
 #pragma unroll
             for (int ks = 0; ks < ((M6A_ABL & 4) ? 0 : kChunk / 8); ++ks) {
               const int kstep = c * (kChunk / 8) + ks;
               const uint64_t bw = dw2 + static_cast<uint64_t>(kstep) * (kStepW2 >> 4);
-              if (kstep == 0) mma_ts(d2, d1, bw, idesc64, 0u);             // [main | corr] = A_hi . [W2_hi ; W2_lo]^T
+              if (ks == 0 && (c == 0 || c == kGroup1Chunk)) mma_ts(d2, d1 + kstep * 8, bw, idesc64, 0u);   // [main | corr] = A_hi . [W2_hi ; W2_lo]^T
               else mma_ts_acc(d2, d1 + kstep * 8, bw, idesc64);
               mma_ts_acc(d2 + kN2, a_lo + ks * 8, bw, idesc32);            // corr += A_lo . W2_hi^T
             }
             mma_commit(&sm.a_free[s]);
             PROF(4);
           }
-          mma_commit(&sm.d2_full[j]);
+          mma_commit(&sm.d2_full[0]);
         }
         if (stop) break;
       }
@@ -432,7 +444,7 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
       }
     };
 
-    // Per iteration t: stage X(t) | prefetch the inputs of tile t+1 | E2 of tile t-2 (its Linear-2 has had two tiles of time).
+    // Per iteration t: E2 of tile t-2 (frees the single D2 buffer as early as possible) | stage X(t) | prefetch tile t+1.
     TileInfo ti_s = next_tile();          // tile staged in this iteration
     TileInfo ti_1, ti_2;                  // tiles t-1, t-2
     ti_1.exists = false;
@@ -442,7 +454,49 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
     PROF_DECL;
     for (uint32_t t = 0;; ++t) {
       const uint32_t b = t & 1u;
-      // ---- (1) stage X(t) (or publish the stop) ---------------------------------------------------------------------------
+      // ---- (1) E2 of tile t-2: this warp's 16 outputs, 8 at a time; the first half finishes the row -------------------------
+      if (ti_2.exists) {
+        const uint32_t u = t - 2, j = u & 1u;
+        const uint32_t d2 = tmem + kColD2 + half * kHalfCols + lane_base;
+        mbar_wait(&sm.d2_full[0], u & 1u, kWaitD2Full);
+        fence_after();
+        PROF(7);
+        float z = 0.0f;
+#pragma unroll
+        for (int o8 = 0; o8 < ((M6A_ABL & 8) ? 0 : kHalfCols); o8 += 8) {
+          uint32_t m0[8], c0[8], m1[8], c1[8];
+          tmem_ld8(d2 + o8, m0);
+          tmem_ld8(d2 + kN2 + o8, c0);
+          tmem_ld8(d2 + 2 * kN2 + o8, m1);
+          tmem_ld8(d2 + 3 * kN2 + o8, c1);
+          wait_ld();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int o = half * kHalfCols + o8 + k;
+            // (main + corr) of each accumulator group, groups added in K order, then the bias: all round-to-nearest float32
+            const float h2 = ((__uint_as_float(m0[k]) + __uint_as_float(c0[k])) + (__uint_as_float(m1[k]) + __uint_as_float(c1[k]))) +
+                             sm.b2[o];
+            z = fmaf(sm.w3[o], fmaxf(h2, 0.0f), z);
+          }
+        }
+        fence_before();
+        mbar_arrive(&sm.d2_free[0]);
+        if (half == 1) sm.zpart[j][row] = z;
+        named_bar_sync(kBarSe, kRoleThreads);
+        PROF(8);
+        if (half == 0) {
+          z = (z + sm.zpart[j][row]) + sm.b3;
+          const float p = 1.0f / (1.0f + expf(-z));
+          if (ti_2.valid) {
+            a.read_prob[ti_2.grow] = p;
+            if (ti_2.lr < kQCap) sm.q[ti_2.slot][ti_2.lr] = 1.0f - p;
+            if (p >= a.read_threshold) atomicAdd(&sm.cnt[ti_2.slot][ti_2.site_l], 1);
+          }
+          if (ti_2.last) mbar_arrive(&sm.slab_full[ti_2.slot]);
+        }
+        PROF(9);
+      }
+      // ---- (2) stage X(t) (or publish the stop) ---------------------------------------------------------------------------
       TileInfo ti_n;
       ti_n.exists = false;
       if (!stop_sent) {
@@ -462,50 +516,13 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
         }
         mbar_arrive(&sm.x_full[b]);
         PROF(4);
-        // ---- (2) the inputs of tile t+1 travel to shared memory meanwhile ----------------------------------------------
+        // ---- (3) the inputs of tile t+1 travel to shared memory meanwhile ----------------------------------------------
         if (ti_s.exists) {
           ti_n = next_tile();
           PROF(5);
           if (!(M6A_ABL & 16)) prefetch_inputs(ti_n, b ^ 1u);
         }
         PROF(6);
-      }
-      // ---- (3) E2 of tile t-2: this warp's 16 outputs; the first half finishes the row ------------------------------------
-      if (ti_2.exists) {
-        const uint32_t u = t - 2, j = u & 1u;
-        const uint32_t d2 = tmem + kColD2 + j * (2 * kN2) + half * kHalfCols + lane_base;
-        mbar_wait(&sm.d2_full[j], (u >> 1) & 1u, kWaitD2Full);
-        fence_after();
-        PROF(7);
-        uint32_t vm[kHalfCols], vc[kHalfCols];
-        if (!(M6A_ABL & 8)) {
-          tmem_ld16(d2, vm);
-          tmem_ld16(d2 + kN2, vc);
-          wait_ld();
-        }
-        fence_before();
-        mbar_arrive(&sm.d2_free[j]);
-        float z = 0.0f;
-#pragma unroll
-        for (int k = 0; k < ((M6A_ABL & 8) ? 0 : kHalfCols); ++k) {
-          const int o = half * kHalfCols + k;
-          const float h2 = (__uint_as_float(vm[k]) + __uint_as_float(vc[k])) + sm.b2[o];
-          z = fmaf(sm.w3[o], fmaxf(h2, 0.0f), z);
-        }
-        if (half == 1) sm.zpart[j][row] = z;
-        named_bar_sync(kBarSe, kRoleThreads);
-        PROF(8);
-        if (half == 0) {
-          z = (z + sm.zpart[j][row]) + sm.b3;
-          const float p = 1.0f / (1.0f + expf(-z));
-          if (ti_2.valid) {
-            a.read_prob[ti_2.grow] = p;
-            if (ti_2.lr < kQCap) sm.q[ti_2.slot][ti_2.lr] = 1.0f - p;
-            if (p >= a.read_threshold) atomicAdd(&sm.cnt[ti_2.slot][ti_2.site_l], 1);
-          }
-          if (ti_2.last) mbar_arrive(&sm.slab_full[ti_2.slot]);
-        }
-        PROF(9);
       }
       // ---- (4) rotate -------------------------------------------------------------------------------------------------------
       ti_2 = ti_1;
@@ -519,8 +536,15 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
     if (half == 0) mbar_arrive(&sm.slab_full[slot]);
   } else {
     // ======================================== Monte-Carlo pooling ============================================================
+    // A warp takes whole sites of a finished slab (w, w + 15, ...): the blocks of 32 * ipl iterations of one site are the
+    // interleaved chains, the block sums are added in block order (the summation order of m6a_kernel.cu: results are
+    // bit-identical functions of the per-read probabilities), and the warp writes the site's outputs itself.  No barrier
+    // between slabs: a warp moves on as soon as its sites are done; the last one releases the slot.
+#if M6A_TC_LAYOUT == 0
     const int mcw = warp == 0 ? 0 : (warp < 4 ? warp - 1 : warp - 17);     // 0, 2, 3, 20..31 -> 0..14
-    const int mct = mcw * 32 + lane;
+#else
+    const int mcw = warp < 12 ? warp : warp - 16;                          // 0..11, 28..30 -> 0..14
+#endif
     const float n_iters_f = static_cast<float>(a.n_iters);
     PROF_DECL;
     for (uint32_t n = 0;; ++n) {
@@ -533,90 +557,69 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
       const bool q_in_smem = m.nr <= kQCap;
       const int* roff = sm.roff[slot];
       const float* q = sm.q[slot];
-      float* partial = partial_base + static_cast<size_t>(slot) * kSlabSites * n_blocks;
 
-      const int items = ns * n_blocks;
       auto lane_rounds = [&](int blk_) {
         const long long it0 = static_cast<long long>(blk_) * ipl * 32 + lane;
         const long long left = (static_cast<long long>(a.n_iters) - it0 + 31) / 32;
         return static_cast<int>(left < 0 ? 0 : (left > ipl ? ipl : left));
       };
-      auto run_single = [&](int item) {
-        const int sl_ = item / n_blocks, blk_ = item - sl_ * n_blocks;
-        const int nreads = roff[sl_ + 1] - roff[sl_];
-        float v = 0.0f;
+      for (int sl = mcw; sl < ((M6A_ABL & 32) ? 0 : ns); sl += kMcWarps) {
+        const int nreads = roff[sl + 1] - roff[sl];
+        const unsigned long long site_id = static_cast<unsigned long long>(a.site_id_base + m.s0 + sl);
+        float total = 0.0f;
         if (nreads > 0) {
-          const int rounds = lane_rounds(blk_);
-          Mwc64x gen;
-          gen.seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk_),
-                   static_cast<unsigned long long>(a.site_id_base + m.s0 + sl_), a.seed);
-          if (q_in_smem) {
-            v = mc_lane_smem<NS>(q + roff[sl_], static_cast<uint32_t>(nreads), gen, rounds);
-          } else {
-            v = mc_lane_generic(a.read_prob + m.r0 + roff[sl_], true, static_cast<uint32_t>(nreads), gen, rounds, NS, nullptr, 0);
-          }
-        }
-        v = warp_butterfly_sum(v);
-        if (lane == 0) partial[sl_ * n_blocks + blk_] = v;
-      };
-      // items (site, block) are dealt round-robin to the warps, kMcChains at a time (interleaved chains)
-      for (int item0 = mcw; item0 < ((M6A_ABL & 32) ? 0 : items); item0 += kMcChains * kMcWarps) {
-        int it[kMcChains], sl[kMcChains], blk[kMcChains], nn[kMcChains];
-        bool all = q_in_smem, paired = false;
+          const bool paired = nreads <= static_cast<int>(kPairedMaxReads);
+          for (int b0 = 0; b0 < n_blocks; b0 += kMcChains) {
+            if (q_in_smem && b0 + kMcChains <= n_blocks) {      // warp-uniform: kMcChains blocks of this site at once
+              uint32_t qa[kMcChains], nu[kMcChains];
+              Mwc64x gen[kMcChains];
+              int rounds[kMcChains];
+              float v[kMcChains];
 #pragma unroll
-        for (int i = 0; i < kMcChains; ++i) {
-          it[i] = item0 + i * kMcWarps;
-          const bool have = it[i] < items;
-          sl[i] = have ? it[i] / n_blocks : 0;
-          blk[i] = have ? it[i] - sl[i] * n_blocks : 0;
-          nn[i] = have ? roff[sl[i] + 1] - roff[sl[i]] : 0;
-          all = all && have && nn[i] > 0;
-          const bool pr = nn[i] <= static_cast<int>(kPairedMaxReads);
-          if (i == 0) paired = pr;
-          all = all && (pr == paired);
-        }
-        if (all) {          // warp-uniform
-          uint32_t qa[kMcChains], nu[kMcChains];
-          Mwc64x gen[kMcChains];
-          int rounds[kMcChains];
-          float v[kMcChains];
+              for (int i = 0; i < kMcChains; ++i) {
+                qa[i] = mc_smem_u32(q + roff[sl]);
+                nu[i] = static_cast<uint32_t>(nreads);
+                rounds[i] = lane_rounds(b0 + i);
+                gen[i].seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(b0 + i), site_id, a.seed);
+                v[i] = 0.0f;
+              }
+              if (paired) mc_rounds_xn<NS, true, kMcChains>(qa, nu, gen, rounds, v);
+              else mc_rounds_xn<NS, false, kMcChains>(qa, nu, gen, rounds, v);
 #pragma unroll
-          for (int i = 0; i < kMcChains; ++i) {
-            qa[i] = mc_smem_u32(q + roff[sl[i]]);
-            nu[i] = static_cast<uint32_t>(nn[i]);
-            rounds[i] = lane_rounds(blk[i]);
-            gen[i].seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk[i]),
-                        static_cast<unsigned long long>(a.site_id_base + m.s0 + sl[i]), a.seed);
-            v[i] = 0.0f;
-          }
-          if (paired) mc_rounds_xn<NS, true, kMcChains>(qa, nu, gen, rounds, v);
-          else mc_rounds_xn<NS, false, kMcChains>(qa, nu, gen, rounds, v);
-#pragma unroll
-          for (int i = 0; i < kMcChains; ++i) {
-            const float w = warp_butterfly_sum(v[i]);
-            if (lane == 0) partial[sl[i] * n_blocks + blk[i]] = w;
-          }
-        } else {
+              for (int i = 0; i < kMcChains; ++i) total += warp_butterfly_sum(v[i]);
+            } else {
 #pragma unroll 1
-          for (int item = item0; item < items && item < item0 + kMcChains * kMcWarps; item += kMcWarps) run_single(item);
+              for (int blk = b0; blk < n_blocks && blk < b0 + kMcChains; ++blk) {
+                const int rounds = lane_rounds(blk);
+                Mwc64x gen;
+                gen.seed(static_cast<uint32_t>(lane), static_cast<uint32_t>(blk), site_id, a.seed);
+                float v;
+                if (q_in_smem) v = mc_lane_smem<NS>(q + roff[sl], static_cast<uint32_t>(nreads), gen, rounds);
+                else v = mc_lane_generic(a.read_prob + m.r0 + roff[sl], true, static_cast<uint32_t>(nreads), gen, rounds, NS, nullptr, 0);
+                total += warp_butterfly_sum(v);
+              }
+            }
+          }
+        }
+        if (lane == 0) {
+          const size_t o = static_cast<size_t>(m.s0 + sl) * a.site_stride;
+          a.site_prob[o] = nreads > 0 ? total / n_iters_f : __int_as_float(0x7fc00000);
+          a.mod_count[o] = sm.cnt[slot][sl];
         }
       }
       PROF(1);
-      named_bar_sync(kBarMc, kMcThreads);
-      PROF(2);
-      if (mct < ns) {
-        const int nreads = roff[mct + 1] - roff[mct];
-        float s = 0.0f;
-        for (int k = 0; k < n_blocks; ++k) s += partial[mct * n_blocks + k];
-        const size_t o = static_cast<size_t>(m.s0 + mct) * a.site_stride;
-        a.site_prob[o] = nreads > 0 ? s / n_iters_f : __int_as_float(0x7fc00000);
-        a.mod_count[o] = sm.cnt[slot][mct];
+      // every warp reports once per slab (also with no site of its own: its slab_full phase must not fall two behind)
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&sm.done[slot], 1) == kMcWarps - 1) {
+          sm.done[slot] = 0;
+          mbar_arrive(&sm.slab_empty[slot]);
+        }
       }
-      named_bar_sync(kBarMc, kMcThreads);
-      if (mct == 0) mbar_arrive(&sm.slab_empty[slot]);
       PROF(3);
     }
-    PROF_STORE(20, mct == 0);
+    PROF_STORE(20, mcw == 0 && lane == 0);
   }
 
   // ---- teardown -----------------------------------------------------------------------------------------------------------

@@ -289,7 +289,7 @@ class NanopolishDS:
             t = self._tables = (np.ascontiguousarray(mean), np.ascontiguousarray(std), kid)
         return t
 
-    def load_sites(self, lo: int, hi: int, n_threads: int = 0) -> SiteBatch:
+    def load_sites(self, lo: int, hi: int, n_threads: int = 0, alloc=None) -> SiteBatch:
         import ctypes as C
         from . import _cabi
         hi = min(hi, len(self))
@@ -312,7 +312,9 @@ class NanopolishDS:
         first[(self._part_ptr[lo:lo + S] - a)[counts > 0]] = 1
         parts["first_of_site"] = first
         R = int(row_off[-1])
-        feats = np.empty((R, 3 * n_pos), dtype=np.float32)
+        # `alloc(shape, dtype)`: where the feature rows live (run_inference passes a page-locked pool so that the H2D copies
+        # of the host-buffer call overlap with the kernel); default: ordinary memory
+        feats = (alloc or np.empty)((R, 3 * n_pos), np.float32)
         read_ids = np.empty(R, dtype=np.int64)
         kmer_idx = np.zeros((S, n_pos), dtype=np.int32)
         mean, std, kid = self._native_tables()

@@ -181,25 +181,45 @@ class MilEngine:
     # ---- host-buffer call (m6a_mil_infer_host_f32): chunked H2D / kernel / D2H pipeline -------------
     def infer_host(self, feats: np.ndarray, read_off: np.ndarray, kmer_idx: Optional[np.ndarray], n_iters: int,
                    seed: int = 0, site_id_base: int = 0, n_samples: int = DEFAULT_N_SAMPLES,
-                   read_threshold: float = 0.033379376, n_chunks: int = 0, out=None
+                   read_threshold: float = 0.033379376, n_chunks: int = 0, out=None, alloc=None
                    ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-        feats = np.ascontiguousarray(feats, dtype=np.float32)
-        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
-        n_sites = len(read_off) - 1
-        if kmer_idx is not None:
-            kmer_idx = np.ascontiguousarray(kmer_idx, dtype=np.int32)
+        """NumPy buffers (page-locked ones overlap H2D / kernel / D2H).  `alloc(shape, dtype)` supplies the output arrays
+        (e.g. _cabi.PinnedPool.empty); default np.empty."""
+        feats, read_off, kmer_idx, n_sites = self._check_host(feats, read_off, kmer_idx, "infer_host")
+        empty = alloc or np.empty
         if out is None:
-            read_prob = np.empty(feats.shape[0], dtype=np.float32)
-            site_prob = np.empty(n_sites, dtype=np.float32)
-            mod_count = np.empty(n_sites, dtype=np.int32)
+            read_prob = empty(feats.shape[0], np.float32)
+            site_prob = empty(n_sites, np.float32)
+            mod_count = empty(n_sites, np.int32)
         else:
             read_prob, site_prob, mod_count = out
+            if not (read_prob.size >= feats.shape[0] and site_prob.size >= n_sites and mod_count.size >= n_sites):
+                raise ValueError("MilEngine.infer_host: output arrays are too small")
         self._select()
         rc = self._lib.m6a_mil_infer_host_f32(
             self._handle, _ptr(feats), _ptr(read_off), _ptr(kmer_idx), n_sites, site_id_base, n_samples, n_iters,
             seed & 0xFFFFFFFFFFFFFFFF, read_threshold, _ptr(read_prob), _ptr(site_prob), _ptr(mod_count), n_chunks)
         _cabi.check(rc, "m6a_mil_infer_host_f32")
         return read_prob, site_prob, mod_count
+
+    def _check_host(self, feats, read_off, kmer_idx, where):
+        """Shape / consistency checks of the host-buffer entry points (the C ABI trusts its arguments)."""
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        if feats.ndim != 2 or feats.shape[1] != 9:
+            raise ValueError(f"MilEngine.{where}: feats must be [reads, 9] float32 (num_neighboring_features = 1), got {feats.shape}")
+        if read_off.ndim != 1 or read_off.size < 1 or read_off[0] != 0 or read_off[-1] != feats.shape[0]:
+            raise ValueError(f"MilEngine.{where}: read_off must be [sites + 1] with read_off[0] == 0 and read_off[-1] == len(feats)")
+        if read_off.size > 1 and np.any(np.diff(read_off) < 0):
+            raise ValueError(f"MilEngine.{where}: read_off must be non-decreasing")
+        n_sites = read_off.size - 1
+        if kmer_idx is not None:
+            kmer_idx = np.ascontiguousarray(kmer_idx, dtype=np.int32)
+            if kmer_idx.shape != (n_sites, 3):
+                raise ValueError(f"MilEngine.{where}: kmer_idx must be [sites, 3] int32, got {kmer_idx.shape}")
+        elif self.weights.emb is not None:
+            raise ValueError(f"MilEngine.{where}: this model has a k-mer embedding, kmer_idx is required")
+        return feats, read_off, kmer_idx, n_sites
 
     # ---- validate()-style literal MIL forward (m6a_mil_validate_f32 / m6a_mil_validate_host_f32) ----------------
     def validate_device(self, feats, read_off, kmer_idx, n_iters: int, seed: int = 0, site_id_base: int = 0,
@@ -252,11 +272,7 @@ class MilEngine:
                       seed: int = 0, site_id_base: int = 0, n_samples: int = DEFAULT_N_SAMPLES, pooling="prod",
                       replace: bool = False, read_threshold: float = 0.033379376, n_chunks: int = 0):
         """NumPy buffers; returns (read_prob [R], bag_prob [sites, n_iters], site_mean [sites], mod_count [sites])."""
-        feats = np.ascontiguousarray(feats, dtype=np.float32)
-        read_off = np.ascontiguousarray(read_off, dtype=np.int64)
-        n_sites = len(read_off) - 1
-        if kmer_idx is not None:
-            kmer_idx = np.ascontiguousarray(kmer_idx, dtype=np.int32)
+        feats, read_off, kmer_idx, n_sites = self._check_host(feats, read_off, kmer_idx, "validate_host")
         read_prob = np.empty(feats.shape[0], dtype=np.float32)
         bag_prob = np.empty((n_sites, n_iters), dtype=np.float32)
         site_prob = np.empty(n_sites, dtype=np.float32)

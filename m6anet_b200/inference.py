@@ -183,9 +183,15 @@ def run_inference(model: MILModel, dl, args):
     Uses args.{out_dir, device, read_proba_threshold, num_iterations, n_processes, seed} like the reference.
     """
     ds = getattr(dl, "dataset", dl)
+    if getattr(ds, "num_neighboring_features", 1) != getattr(model, "num_neighboring_features", 1):
+        raise ValueError("run_inference: the dataset was built with num_neighboring_features = %r but the model expects %r"
+                         % (getattr(ds, "num_neighboring_features", 1), getattr(model, "num_neighboring_features", 1)))
     rank, world, local_rank = env_world()
     dev = _resolve_device(args.device, local_rank, world)
-    if world > 1:     # torch only for the multi-GPU plumbing (torch.distributed over NCCL)
+    # M6A_DIST_BACKEND=gloo: the one all-gather runs on host tensors, so several ranks may share one GPU (tests on a
+    # single-GPU box); default NCCL over NVLink
+    backend = os.environ.get("M6A_DIST_BACKEND", "nccl")
+    if world > 1:     # torch only for the multi-GPU plumbing (torch.distributed)
         import torch
         import torch.distributed as dist
         if os.environ.get("M6A_NO_NUMA_BIND") != "1":
@@ -194,7 +200,10 @@ def run_inference(model: MILModel, dl, args):
         torch.cuda.set_device(dev)
         if not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+            if backend == "nccl":
+                dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+            else:
+                dist.init_process_group(backend)
     seed = int(getattr(args, "seed", 0))
     n_iters = int(args.num_iterations)
     thr = float(args.read_proba_threshold)
@@ -210,6 +219,12 @@ def run_inference(model: MILModel, dl, args):
     suffix = f".rank{rank}" if world > 1 else ""
     all_sp, all_mc = [], []
     eng = model.engine(dev)
+    from ._cabi import PinnedPool
+    pool = PinnedPool()       # page-locked feature / output buffers, recycled batch to batch (H2D / D2H overlap the kernel)
+    if world > 1:             # a direct call may find shard files of an earlier, failed run: they are opened for append
+        for path in (site_path, indiv_path):
+            if os.path.exists(path + suffix):
+                os.remove(path + suffix)
 
     # Three overlapped stages (the native calls release the GIL): ingest of batch i+1 | H2D/kernel/D2H of batch i |
     # CSV emit of batch i-1.  Queues are bounded so at most ~3 batches are resident on the host.
@@ -224,7 +239,7 @@ def run_inference(model: MILModel, dl, args):
             for a, b in spans:
                 if errors:
                     break
-                q_in.put((a, ds.load_sites(a, b, n_threads=n_threads)))        # data.json -> flat buffers (native)
+                q_in.put((a, ds.load_sites(a, b, n_threads=n_threads, alloc=pool.empty)))   # data.json -> flat buffers (native)
         except BaseException as e:   # noqa: BLE001 - re-raised in the main thread
             errors.append(e)
         finally:
@@ -240,6 +255,7 @@ def run_inference(model: MILModel, dl, args):
                     batch, read_prob, site_prob, mod_count = item
                     write_site_rows(f, batch, site_prob, mod_count, n_threads)
                     write_indiv_rows(g, batch, read_prob, n_threads)
+                    pool.give_back(batch.feats, read_prob)
         except BaseException as e:   # noqa: BLE001
             errors.append(e)
             while q_out.get() is not None:    # keep draining so the main thread never blocks on a full queue
@@ -257,9 +273,11 @@ def run_inference(model: MILModel, dl, args):
             a, batch = item
             if errors:
                 continue
-            read_prob, site_prob, mod_count = eng.infer_host(batch.feats, batch.read_off, batch.kmer_idx, n_iters,
-                                                             seed=seed, site_id_base=a, n_samples=N_SAMPLES,
-                                                             read_threshold=thr)    # H2D -> kernel -> D2H
+            read_prob = pool.empty(batch.feats.shape[0], np.float32)
+            site_prob = np.empty(batch.n_sites, np.float32)
+            mod_count = np.empty(batch.n_sites, np.int32)
+            eng.infer_host(batch.feats, batch.read_off, batch.kmer_idx, n_iters, seed=seed, site_id_base=a,
+                           n_samples=N_SAMPLES, read_threshold=thr, out=(read_prob, site_prob, mod_count))   # H2D -> kernel -> D2H
             all_sp.append(site_prob)
             all_mc.append(mod_count)
             q_out.put((batch, read_prob, site_prob, mod_count))
@@ -271,14 +289,25 @@ def run_inference(model: MILModel, dl, args):
         q_out.put(None)
         t_in.join()
         t_out.join()
+    if world > 1:
+        # every rank learns whether any rank failed BEFORE the collective: a rank that raised alone would leave the others
+        # blocked in the all-gather until the watchdog fires
+        import torch.distributed as dist
+        tdev = torch.device("cuda", dev) if backend == "nccl" else torch.device("cpu")
+        failed = torch.tensor([1 if errors else 0], dtype=torch.int32, device=tdev)
+        dist.all_reduce(failed, op=dist.ReduceOp.MAX)
+        if int(failed.item()) and not errors:
+            errors.append(RuntimeError("run_inference: another rank failed; see its traceback"))
+        if errors:
+            for path in (site_path, indiv_path):
+                if os.path.exists(path + suffix):
+                    os.remove(path + suffix)
     if errors:
         raise errors[0]
     site_prob = np.concatenate(all_sp) if all_sp else np.zeros(0, np.float32)
     mod_count = np.concatenate(all_mc) if all_mc else np.zeros(0, np.int32)
 
     if world > 1:
-        import torch.distributed as dist
-        tdev = torch.device("cuda", dev)
         sp_t, mc_t = all_gather_site_outputs(torch.from_numpy(site_prob).to(tdev), torch.from_numpy(mod_count).to(tdev), bounds)
         site_prob, mod_count = sp_t.cpu().numpy(), mc_t.cpu().numpy()
         dist.barrier()

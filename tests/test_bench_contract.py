@@ -24,9 +24,30 @@ def test_reference_arm_line():
     d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--sites", "3000", "--cpu-sample-sites", "3000")
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
     assert d["metric"] == "DRACH sites/sec at num_iterations=1000" and d["unit"] == "sites/s" and d["higher_is_better"] is True
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the reference's own code (oracle/_ref, installed by oracle/make_ref.sh) when it is there, else the oracle's port
+    ref_there = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "m6anet"))
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == ("reference" if ref_there else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_both_arms_print_the_same_config():
+    """The driver compares the `config` of the two arms: it is a function of the command line only."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    argv = sys.argv
+    try:
+        sys.argv = ["bench.py", "--gpus", "1", "--steps", "2"]
+        a = bench.parse_args()
+        sys.argv = ["bench.py", "--gpus", "1", "--steps", "2", "--impl", "reference"]
+        b = bench.parse_args()
+    finally:
+        sys.argv = argv
+    assert bench.config_dict(a) == bench.config_dict(b)
+    assert bench.config_dict(a)["sites"] == 1_000_000 and bench.config_dict(a)["reads_per_site"] == 50
+    assert {c: bench.CONFIGS[c]["sites"] for c in bench.CONFIGS} == {2: 100_000, 3: 1_000_000, 4: 500_000, 5: 250_000}
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -39,14 +60,17 @@ def test_reference_arm_other_ranks_exit_quietly():
 @pytest.mark.gpu
 def test_b200_arm_line():
     d = run_bench("--steps", "3", "--warmup", "3", "--sites", "60000", "--cpu-sample-sites", "2000")
-    assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
+    assert BASE_KEYS | {"roofline", "clocks", "parity", "result_digest"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"] == "fp32" and d["data"] == "synthetic" and d["vs_baseline"] is None
-    assert d["value"] > 1e6 and d["gpu_launches"] == 6     # tile_bounds_kernel + mil_infer_kernel per step
+    assert d["value"] > 1e6 and d["gpu_launches"] == 6     # tile_bounds_kernel + mil_infer(_tc)_kernel per step
+    assert d["parity"]["ok"] is True and d["parity"]["sites"] >= 50_000 and d["parity"]["mod_count_mismatch"] == 0
+    assert d["parity"]["max_abs_site"] <= 1e-4 and d["parity"]["max_abs_read"] <= 3e-6
+    assert len(d["result_digest"]["site_prob_mod_count_sha256"]) == 64 and len(d["result_digest"]["read_prob_sha256"]) == 64
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     assert rf["algorithmic_bytes_per_launch"] == 60000 * 2028
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 60000 * 50 * 36 and e["d2h_bytes_per_step"] > 60000 * 50 * 4
     assert e["matches_resident_path"] is True
-    assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -393,9 +393,14 @@ def test_validate_host_path_equals_device_path_and_ignores_sharding(synthetic_in
     a = eng.validate_host(feats[:off[cut]], off[:cut + 1], kmer[:cut], 12, seed=5)
     b = eng.validate_host(feats[off[cut]:], off[cut:] - off[cut], kmer[cut:], 12, seed=5, site_id_base=cut)
     assert np.array_equal(np.concatenate([a[1], b[1]]), bag)
-    # the inference entry point is untouched by the bags instantiation
+    # the inference entry point with the same (CUDA-core) read encoder gives the same per-read probabilities bit for bit;
+    # with the tensor-core encoder they agree to float32 round-off
+    eng.set_encoder("ffma")
     irp, isp, imc = eng.infer_host(feats, off, kmer, 100, seed=5)
     assert np.array_equal(irp, rp) and np.array_equal(imc, mc) and np.isfinite(isp).all()
+    eng.set_encoder("tc")
+    irp, isp, imc = eng.infer_host(feats, off, kmer, 100, seed=5)
+    assert np.max(np.abs(irp - rp)) <= 2e-6 and np.isfinite(isp).all()
 
 
 @pytest.mark.gpu

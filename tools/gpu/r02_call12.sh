@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02_pytest_gpu.log
+for c in 2 4 5; do timeout 600 python bench.py --config $c --steps 20 --warmup 5 > gpurun_out/r02_bench_cfg$c.json 2> gpurun_out/r02_bench_cfg$c.err; echo "bench cfg$c rc=$?"; done
+timeout 600 python bench.py --encoder ffma --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02_bench_cfg3_ffma.json 2>/dev/null
+timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_ref.err; echo "ref rc=$?"
+python - <<'PY'
+import json
+for f in ['cfg2','cfg4','cfg5','cfg3_ffma','reference_arm']:
+    try:
+        d=json.loads(open(f'gpurun_out/r02_bench_{f}.json').read().strip().splitlines()[-1])
+        print(f, round(d['value']/1e6,3), 'M sites/s', round(d['ms_per_step'],3), 'ms', (d.get('parity') or {}).get('ok'), (d.get('e2e') or {}).get('value'), (d.get('cpu_baseline') or {}).get('kind'))
+    except Exception as e: print(f, 'ERR', e)
+PY

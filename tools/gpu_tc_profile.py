@@ -35,7 +35,7 @@ roles = [
                                    "wait d2_full", "E2 ld + z + bar", "E2 sigmoid + outputs"]),
     ("MMA issuer", 10, ["wait x_full", "L1 issue+commit", "wait d2_free", "wait a_full (5x)", "L2 issue+commit (5x)"]),
     ("E1 thread 0", 30, ["wait l1_done", "tmem_ld+wait (5x)", "relu/split (5x)", "wait a_free (5x)", "tmem_st+wait+arrive (5x)"]),
-    ("MC thread 0", 20, ["wait slab_full", "items", "bar", "finalize+bar+arrive"]),
+    ("MC warp 0", 20, ["wait slab_full", "sites of the slab", "-", "report"]),
 ]
 print(f"sites {S} iters {iters}: ~{tiles:.0f} MMA tiles per CTA; cycles per tile (block 0):")
 for name, base, phases in roles:
