@@ -110,19 +110,40 @@ def algorithmic_bytes_per_site(n_reads: int) -> int:
     return n_reads * 36 + 12 + 8 + n_reads * 4 + 8
 
 
-def synth_shard(site_a: int, site_b: int, n_reads: int, seed_tag: int, ragged: bool = False):
-    """Synthetic shard [site_a, site_b): N(0,1) features, uniform valid k-mer ids."""
-    rng = np.random.default_rng([0, seed_tag, site_a])
+def _synth_block(block: int, site_a: int, site_b: int, n_reads: int, seed_tag: int, ragged: bool):
+    """One generation block [site_a, site_b): N(0,1) features, uniform valid k-mer ids."""
+    rng = np.random.default_rng([0, seed_tag, block])
     ns = site_b - site_a
     if ragged:
         n = np.clip(np.round(np.exp(rng.normal(np.log(33), 0.8, size=ns))), 20, 1000).astype(np.int64)
-        read_off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
-        feats = rng.standard_normal((int(read_off[-1]), 9), dtype=np.float32)
-        return feats, read_off, rng.integers(0, 66, size=(ns, 3), dtype=np.int32)
+        feats = rng.standard_normal((int(n.sum()), 9), dtype=np.float32)
+        return feats, n, rng.integers(0, 66, size=(ns, 3), dtype=np.int32)
     feats = rng.standard_normal((ns * n_reads, 9), dtype=np.float32)
-    read_off = np.arange(ns + 1, dtype=np.int64) * n_reads
-    kmer = rng.integers(0, 66, size=(ns, 3), dtype=np.int32)
-    return feats, read_off, kmer
+    return feats, np.full(ns, n_reads, dtype=np.int64), rng.integers(0, 66, size=(ns, 3), dtype=np.int32)
+
+
+def synth_shard(site_a: int, site_b: int, n_reads: int, seed_tag: int, ragged: bool = False, total_sites: int = 0):
+    """Sites [site_a, site_b) of THE job.  The job is generated in DIGEST_BLOCKS fixed blocks of sites, each from its own
+    seed, so that every sharding (N = 1, 2, 4, 8, or any other) scores bit-identical inputs; a shard generates the blocks it
+    overlaps and keeps its slice."""
+    total = total_sites or site_b
+    edges = [total * b // DIGEST_BLOCKS for b in range(DIGEST_BLOCKS + 1)]
+    fs, ns_, ks = [], [], []
+    for b in range(DIGEST_BLOCKS):
+        lo, hi = edges[b], edges[b + 1]
+        if hi <= site_a or lo >= site_b or hi == lo:
+            continue
+        f, n, k = _synth_block(b, lo, hi, n_reads, seed_tag, ragged)
+        a_, b_ = max(site_a, lo) - lo, min(site_b, hi) - lo
+        off = np.concatenate([[0], np.cumsum(n)])
+        fs.append(f[off[a_]:off[b_]])
+        ns_.append(n[a_:b_])
+        ks.append(k[a_:b_])
+    if not fs:
+        return np.zeros((0, 9), np.float32), np.zeros(1, np.int64), np.zeros((0, 3), np.int32)
+    n_all = np.concatenate(ns_)
+    read_off = np.concatenate([[0], np.cumsum(n_all)]).astype(np.int64)
+    return np.ascontiguousarray(np.concatenate(fs)), read_off, np.ascontiguousarray(np.concatenate(ks))
 
 
 def peaks():
@@ -210,7 +231,7 @@ def run_reference(a):
         return 0
     from oracle.cpu_baseline import host_cores
     n_sample = min(a.sites, a.cpu_sample_sites)
-    feats, off, kmer = synth_shard(0, n_sample, a.reads, 0)
+    feats, off, kmer = synth_shard(0, n_sample, a.reads, 1, total_sites=a.sites)
     cores = host_cores()
     for _ in range(min(a.warmup, 1)):
         cpu_reference_run(a, feats, off, kmer, cores)
@@ -332,7 +353,7 @@ def main():
     sa, sb = bounds[rank], bounds[rank + 1]
     ns = sb - sa
     shard_max = max(bounds[r + 1] - bounds[r] for r in range(world))
-    feats_h, off_h, kmer_h = synth_shard(sa, sb, a.reads, 1, a.ragged)
+    feats_h, off_h, kmer_h = synth_shard(sa, sb, a.reads, 1, a.ragged, total_sites=a.sites)
     thr = MODELS[a.model][1]
     eng = MilEngine(W.from_npz(os.path.join(ROOT, "m6anet_b200", "assets", "model_states", MODELS[a.model][0])), dev)
     if a.encoder:

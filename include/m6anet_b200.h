@@ -114,7 +114,7 @@ int m6a_model_set_encoder(m6a_model_t *model, int32_t encoder);
 int m6a_model_get_encoder(const m6a_model_t *model);
 /* Debug aid: arms (first call) and reads the trap record of the tensor-core kernel -- {wait site, block, thread, parity}
  * of a bounded mbarrier wait that gave up, kept in mapped host memory so that it survives the trap. */
-int m6a_debug_trap_record(m6a_model_t *model, int32_t *out4);
+int m6a_debug_trap_record(m6a_model_t *model, int32_t *out64);   /* 16 wait sites x {site, block, thread, parity} */
 /* Page-locked host memory (cudaHostAlloc, portable) for the host-buffer entry points: the H2D / D2H copies of
  * m6a_mil_infer_host_f32 only overlap with the kernel when its buffers are pinned. */
 int m6a_pinned_alloc(void **out, int64_t bytes);
@@ -253,6 +253,14 @@ int m6a_ingest_parts(const char *const *paths, int32_t n_files, const m6a_part_t
                      int32_t n_flank, const double *norm_mean, const double *norm_std,
                      const int32_t *kmer_id, float *feats, int64_t *read_ids, int32_t *kmer_idx,
                      int32_t n_threads, int64_t *bad_part);
+
+/* The same, and every part's line must carry the keys of its site: tx_buf/tx_off = concatenated transcript ids + CSR offsets
+ * [n_sites + 1], tx_pos [n_sites] (the reference looks the line up by json.loads(line)[tx_id][str(tx_pos)] and raises KeyError
+ * on a stale data.info, utils/data_utils.py:185); a mismatch is M6A_EPARSE.  Replicates of a site must also agree on the 7-mer. */
+int m6a_ingest_parts_keyed(const char *const *paths, int32_t n_files, const m6a_part_t *parts, int64_t n_parts,
+                           int32_t n_flank, const double *norm_mean, const double *norm_std,
+                           const int32_t *kmer_id, const char *tx_buf, const int64_t *tx_off, const int64_t *tx_pos,
+                           float *feats, int64_t *read_ids, int32_t *kmer_idx, int32_t n_threads, int64_t *bad_part);
 
 /* data.info reader (csv with a header naming transcript_id, transcript_position, start, end, n_reads; reference
  * utils/data_utils.py:118-129 reads it with pandas).  m6a_info_count sizes the buffers, m6a_info_read fills them:

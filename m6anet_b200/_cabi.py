@@ -19,7 +19,7 @@ EXPORTS = (
     "m6a_mil_infer_f32", "m6a_mil_infer_packed_f32", "m6a_model_set_encoder", "m6a_model_get_encoder", "m6a_debug_trap_record",
     "m6a_pinned_alloc", "m6a_pinned_free", "m6a_build_info",
     "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_mil_validate_f32", "m6a_mil_validate_host_f32", "m6a_sample_bags",
-    "m6a_last_launch", "m6a_ingest_parts", "m6a_info_count", "m6a_info_read",
+    "m6a_last_launch", "m6a_ingest_parts", "m6a_ingest_parts_keyed", "m6a_info_count", "m6a_info_read",
     "m6a_write_site_csv",
     "m6a_write_indiv_csv",
 )
@@ -120,6 +120,9 @@ def lib() -> C.CDLL:
     L.m6a_last_launch.argtypes = [C.POINTER(i32)] * 5
     L.m6a_ingest_parts.restype = C.c_int
     L.m6a_ingest_parts.argtypes = [C.POINTER(C.c_char_p), i32, vp, i64, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(i64)]
+    L.m6a_ingest_parts_keyed.restype = C.c_int
+    L.m6a_ingest_parts_keyed.argtypes = [C.POINTER(C.c_char_p), i32, vp, i64, i32, vp, vp, vp, C.c_char_p, vp, vp, vp, vp, vp, i32,
+                                         C.POINTER(i64)]
     L.m6a_info_count.restype = C.c_int
     L.m6a_info_count.argtypes = [C.c_char_p, C.POINTER(i64), C.POINTER(i64)]
     L.m6a_info_read.restype = C.c_int

@@ -226,14 +226,14 @@ extern "C" int m6a_model_get_encoder(const m6a_model_t* model) {
 extern "C" int m6a_debug_trap_record(m6a_model_t* model, int32_t* out4) {
   if (!model) return M6A_EINVAL;
   if (!model->trap_record) {
-    M6A_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&model->trap_record), 64, cudaHostAllocMapped));
-    memset(model->trap_record, 0, 64);
+    M6A_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&model->trap_record), 256, cudaHostAllocMapped));
+    memset(model->trap_record, 0, 256);
     int* dptr = nullptr;
     M6A_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), model->trap_record, 0));
     M6A_CUDA(tc_set_trap_record(dptr));
   }
-  if (out4)
-    for (int i = 0; i < 4; ++i) out4[i] = model->trap_record[i];
+  if (out4)       // 16 wait sites x {site, block, thread, parity}; the caller's buffer holds 64 int32
+    for (int i = 0; i < 64; ++i) out4[i] = model->trap_record[i];
   return M6A_OK;
 }
 

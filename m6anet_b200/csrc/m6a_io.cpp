@@ -57,6 +57,12 @@ struct IngestCtx {
   float* feats;
   int64_t* read_ids;
   int32_t* kmer_idx;
+  // optional keys of the sites (m6a_ingest_parts_keyed): the line of every part must carry its site's transcript id and
+  // position (the reference indexes json.loads(line)[tx_id][str(tx_pos)] and raises KeyError on a stale index)
+  const char* tx_buf = nullptr;
+  const int64_t* tx_off = nullptr;
+  const int64_t* tx_pos = nullptr;
+  std::vector<int32_t> part_ids;     // five-mer ids seen by every part (replicates of a site must agree)
   std::vector<int> fds;
   std::atomic<int64_t> next{0};
   std::atomic<int64_t> bad{-1};
@@ -184,12 +190,19 @@ bool parse_part(IngestCtx& c, int64_t pi, std::vector<char>& buf) {
   buf[len] = 0;
   const char* e = buf.data() + len;
   // {"tx":{"pos":{"KMER":[
-  const char *t0, *t1, *k0, *k1;
+  const char *t0, *t1, *q0 = nullptr, *q1 = nullptr, *k0, *k1;
   const char* r = expect(buf.data(), e, '{');
   if (r) r = expect_string(r, e, &t0, &t1);
   if (r) r = expect(r, e, ':');
   if (r) r = expect(r, e, '{');
-  if (r) r = expect_string(r, e, &t0, &t1);
+  if (r) r = expect_string(r, e, &q0, &q1);
+  if (r && c.tx_buf != nullptr) {                       // keys of the line == keys of the data.info row
+    const int64_t a = c.tx_off[p.site], b = c.tx_off[p.site + 1];
+    if (t1 - t0 != b - a || memcmp(t0, c.tx_buf + a, static_cast<size_t>(b - a)) != 0) return false;
+    char num[24];
+    const int nl = snprintf(num, sizeof num, "%lld", static_cast<long long>(c.tx_pos[p.site]));
+    if (q1 - q0 != nl || memcmp(q0, num, static_cast<size_t>(nl)) != 0) return false;
+  }
   if (r) r = expect(r, e, ':');
   if (r) r = expect(r, e, '{');
   if (r) r = expect_string(r, e, &k0, &k1);
@@ -258,6 +271,8 @@ bool parse_part(IngestCtx& c, int64_t pi, std::vector<char>& buf) {
     int32_t* kid = c.kmer_idx + p.site * n_pos;
     for (int j = 0; j < n_pos; ++j) kid[j] = ids[j];
   }
+  if (!c.part_ids.empty())
+    for (int j = 0; j < n_pos; ++j) c.part_ids[static_cast<size_t>(pi) * 11 + j] = ids[j];
   return true;
 }
 
@@ -360,13 +375,15 @@ int format_parallel(int fd, int64_t n_sites, int32_t n_threads, F&& format_range
 
 }  // namespace
 
-extern "C" int m6a_ingest_parts(const char* const* paths, int32_t n_files, const m6a_part_t* parts, int64_t n_parts,
-                                int32_t n_flank, const double* norm_mean, const double* norm_std, const int32_t* kmer_id,
-                                float* feats, int64_t* read_ids, int32_t* kmer_idx, int32_t n_threads, int64_t* bad_part) {
+extern "C" int m6a_ingest_parts_keyed(const char* const* paths, int32_t n_files, const m6a_part_t* parts, int64_t n_parts,
+                                      int32_t n_flank, const double* norm_mean, const double* norm_std, const int32_t* kmer_id,
+                                      const char* tx_buf, const int64_t* tx_off, const int64_t* tx_pos, float* feats,
+                                      int64_t* read_ids, int32_t* kmer_idx, int32_t n_threads, int64_t* bad_part) {
   if (bad_part) *bad_part = -1;
   if (n_parts < 0 || n_files < 0 || n_flank < 0 || n_flank > 5) return M6A_EINVAL;
   if (n_parts == 0) return M6A_OK;
   if (!paths || !parts || !norm_mean || !norm_std || !kmer_id || !feats || !read_ids || !kmer_idx) return M6A_EINVAL;
+  if ((tx_buf != nullptr) != (tx_off != nullptr) || (tx_buf != nullptr) != (tx_pos != nullptr)) return M6A_EINVAL;
   IngestCtx c;
   c.paths = paths;
   c.parts = parts;
@@ -378,6 +395,12 @@ extern "C" int m6a_ingest_parts(const char* const* paths, int32_t n_files, const
   c.feats = feats;
   c.read_ids = read_ids;
   c.kmer_idx = kmer_idx;
+  c.tx_buf = tx_buf;
+  c.tx_off = tx_off;
+  c.tx_pos = tx_pos;
+  bool multi = false;
+  for (int64_t i = 0; i < n_parts && !multi; ++i) multi = parts[i].first_of_site == 0;
+  if (multi) c.part_ids.assign(static_cast<size_t>(n_parts) * 11, -1);
   for (int f = 0; f < n_files; ++f) {
     const int fd = open(paths[f], O_RDONLY);
     if (fd < 0) {
@@ -396,8 +419,29 @@ extern "C" int m6a_ingest_parts(const char* const* paths, int32_t n_files, const
   for (int t = 0; t < nw; ++t) th.emplace_back(ingest_worker, &c);
   for (auto& x : th) x.join();
   for (int g : c.fds) close(g);
+  // every replicate of a site must describe the same 7-mer (the reference asserts it, utils/data_utils.py:418)
+  if (multi && c.status.load() == M6A_OK) {
+    const int n_pos = 2 * n_flank + 1;
+    for (int64_t i = 0; i < n_parts; ++i) {
+      if (parts[i].first_of_site) continue;
+      const int32_t* kid = kmer_idx + parts[i].site * n_pos;
+      for (int j = 0; j < n_pos; ++j)
+        if (c.part_ids[static_cast<size_t>(i) * 11 + j] != kid[j]) {
+          fail(c, i, M6A_EPARSE);
+          break;
+        }
+      if (c.status.load() != M6A_OK) break;
+    }
+  }
   if (bad_part) *bad_part = c.bad.load();
   return c.status.load();
+}
+
+extern "C" int m6a_ingest_parts(const char* const* paths, int32_t n_files, const m6a_part_t* parts, int64_t n_parts,
+                                int32_t n_flank, const double* norm_mean, const double* norm_std, const int32_t* kmer_id,
+                                float* feats, int64_t* read_ids, int32_t* kmer_idx, int32_t n_threads, int64_t* bad_part) {
+  return m6a_ingest_parts_keyed(paths, n_files, parts, n_parts, n_flank, norm_mean, norm_std, kmer_id, nullptr, nullptr, nullptr,
+                                feats, read_ids, kmer_idx, n_threads, bad_part);
 }
 
 // ---- data.info reader: csv with a header naming transcript_id,transcript_position,start,end,n_reads (any order,

@@ -61,7 +61,7 @@ constexpr uint32_t kColD1 = 0, kColALo = 2 * kN1, kColD2 = 2 * kN1 + 2 * kChunk;
 constexpr int kGroups = 2;                   // Linear-2 accumulator groups (chunks 0..2 | 3..4), each [main 32 | corr 32]
 constexpr int kGroup1Chunk = 3;              // first chunk of the second group
 static_assert(kColD2 + kGroups * 2 * kN2 == kTmemCols, "TMEM column budget");
-constexpr int kBarSe = 1;                    // named barrier of the staging / E2 role
+constexpr int kBarSe = 1, kBarE1 = 3;        // named barriers: staging / E2 groups (1, 2), E1 role (3)
 constexpr int kHalfCols = kChunk / 2;        // columns of a chunk per warp
 constexpr int kCtrlRing = 8;                 // per-tile control words (the staging warps run at most 4 tiles ahead of E1)
 
@@ -86,7 +86,6 @@ struct alignas(128) TcSmem {
   float x[2][2][kK1 / 4][kTileM][4];            // 32 KB   A of Linear-1: [buffer][hi, lo][k-chunk][row][4]
   float fbuf[2][kTileM][kK1];                   // 16 KB   prefetched inputs of the next tile (cp.async), [x(9) | emb | 1]
   float q[kSlots][kQCap];                       // 48 KB   q = 1 - p of a slab
-  float zpart[2][kTileM];                       // partial logits of the second half of the outputs
   float b2[kN2];
   float w3[kN2];
   float b3;
@@ -101,11 +100,14 @@ struct alignas(128) TcSmem {
   alignas(8) unsigned long long l1_done[2];     // MMA commit    -> E1, staging : D1[b] ready / X[b] consumed
   alignas(8) unsigned long long a_full[2];      // E1 (256)      -> MMA : chunk staged in D1 (hi) / A_lo slot
   alignas(8) unsigned long long a_free[2];      // MMA commit    -> E1 : A_lo slot consumed
-  alignas(8) unsigned long long d2_full[1];     // MMA commit    -> E2 : D2 complete (both accumulator groups)
+  alignas(8) unsigned long long d2_full[2];     // MMA commit    -> E2 group (tile parity) : D2 complete.  One barrier per
+                                                // group: a parity wait must never be posted a phase early, and the groups
+                                                // take turns
   alignas(8) unsigned long long d2_free[1];     // E2 (256)      -> MMA : D2 read out
   int done[kSlots];                             // MC warps finished with the slab of a slot
   alignas(8) unsigned long long slab_full[kSlots];   // E2 (128) -> MC
   alignas(8) unsigned long long slab_empty[kSlots];  // MC (1)   -> staging
+  alignas(8) unsigned long long hdr_ready[kSlots];   // staging group that opened the slab (128) -> the other group
 };
 static_assert(offsetof(TcSmem, w1lo) % 128 == 0 && offsetof(TcSmem, w2s) % 128 == 0 && offsetof(TcSmem, x) % 128 == 0,
               "UMMA operands must start on a 128-byte core-matrix boundary");
@@ -137,7 +139,7 @@ __device__ unsigned long long g_prof[40];
 // wait sites (trap record)
 enum WaitSite : int {
   kWaitXFull = 1, kWaitL1Done, kWaitAFull, kWaitAFree, kWaitD2Full, kWaitD2Free, kWaitSlabFull, kWaitSlabEmpty,
-  kWaitXFullE1, kWaitL1DoneSe
+  kWaitXFullE1, kWaitL1DoneSe, kWaitHdr
 };
 
 struct TileInfo {      // one MMA tile of 128 rows, as seen by the staging / E2 thread that owns row `row`
@@ -150,6 +152,25 @@ struct TileInfo {      // one MMA tile of 128 rows, as seen by the staging / E2 
 
 __device__ __forceinline__ float rn_tf32(float v) {     // round to nearest (ties away), low 13 mantissa bits zero
   return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+}
+
+// Role-wide wait on an mbarrier: ONE lane of the role's first warp polls it, the other warps of the role sleep in a
+// hardware barrier.  (Eight warps polling try_wait cost ~30 % of the SM's issue slots while the pipeline waits for the
+// Monte-Carlo warps -- ncu, profiles/r02_tc_abl30_*: the Monte-Carlo warps lose exactly those slots.)
+#ifndef M6A_ROLE_WAIT
+#define M6A_ROLE_WAIT 0     // measured: the extra barrier hop costs more than the polls it saves (13.65 vs 12.67 ms)
+#endif
+__device__ __forceinline__ void role_wait(unsigned long long* bar, uint32_t parity, int site, bool leader_warp, int lane,
+                                          int bar_id, int n_threads) {
+#if M6A_ROLE_WAIT
+  if (leader_warp) {
+    if (lane == 0) mbar_wait(bar, parity, site);
+    __syncwarp();
+  }
+  named_bar_sync(bar_id, n_threads);
+#else
+  mbar_wait(bar, parity, site);
+#endif
 }
 
 template <int NS>
@@ -172,16 +193,18 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
     if (tid == 0) {
       sm.b3 = image->b3;
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&sm.x_full[i], kRoleThreads);
+        mbar_init(&sm.x_full[i], kTileM);
         mbar_init(&sm.l1_done[i], 1);
         mbar_init(&sm.a_full[i], kRoleThreads);
         mbar_init(&sm.a_free[i], 1);
       }
       mbar_init(&sm.d2_full[0], 1);
-      mbar_init(&sm.d2_free[0], kRoleThreads);
+      mbar_init(&sm.d2_full[1], 1);
+      mbar_init(&sm.d2_free[0], kTileM);
       for (int i = 0; i < kSlots; ++i) {
         mbar_init(&sm.slab_full[i], kTileM);
         mbar_init(&sm.slab_empty[i], 1);
+        mbar_init(&sm.hdr_ready[i], kTileM);
         sm.done[i] = 0;
       }
       fence_barrier_init();
@@ -257,7 +280,7 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
             mma_commit(&sm.a_free[s]);
             PROF(4);
           }
-          mma_commit(&sm.d2_full[0]);
+          mma_commit(&sm.d2_full[j]);
         }
         if (stop) break;
       }
@@ -273,7 +296,7 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
     for (uint32_t t = 0;; ++t) {
       const uint32_t b = t & 1u;
       // (not x_full: the staging warps may run two phases of it ahead of this role, and a parity wait cannot lag by two)
-      mbar_wait(&sm.l1_done[b], (t >> 1) & 1u, kWaitL1Done);
+      role_wait(&sm.l1_done[b], (t >> 1) & 1u, kWaitL1Done, warp == kE1Warp0, lane, kBarE1, kRoleThreads);
       if (sm.x_ctrl[t % kCtrlRing] == 0) break;                  // the MMA issuer arrives on l1_done for the stop tile too
       fence_after();
       PROF(0);
@@ -297,7 +320,7 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
           }
         }
         PROF(2);
-        mbar_wait(&sm.a_free[s], ((g >> 1) & 1u) ^ 1u, kWaitAFree);      // the MMAs of chunk g-2 have read this A_lo slot
+        role_wait(&sm.a_free[s], ((g >> 1) & 1u) ^ 1u, kWaitAFree, warp == kE1Warp0, lane, kBarE1, kRoleThreads);   // the MMAs of chunk g-2 have read this A_lo slot
         fence_after();
         PROF(3);
         if (!(M6A_ABL & 2)) {
@@ -313,55 +336,66 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
     PROF_STORE(30, et == 0);
   } else if (warp >= kSeWarp0 && warp < kSeWarp0 + kRoleWarps) {
     // ======================================== staging of X + E2 (sigmoid, outputs) =========================================
-    const int et = tid - kSeWarp0 * 32;                         // 0..255
-    const int row = et & (kTileM - 1);                          // row of the tile = TMEM lane
-    const int half = et >> 7;                                   // which 8 inputs / which 16 outputs
+    // Two groups of 4 warps (one warp per TMEM lane quadrant, thread = row of the tile) take the tiles alternately: group 0
+    // the even ones, group 1 the odd ones -- X[b], x_full[b] and every second use of D2 belong to group b.  The per-tile work of
+    // this role is a serial chain (TMEM read -> sigmoid -> outputs -> staging -> prefetch) about twice as long as the tensor
+    // pipe needs for a tile; two groups hide it.  Tiles are dealt statically (tile = blockIdx.x + k * gridDim.x), so both
+    // groups walk the same slab sequence on their own; the group that meets a slab first (the parity of the slab's first MMA
+    // tile) opens it and the other waits for hdr_ready.
+    const int grp = (warp - kSeWarp0) >> 2;                     // 0 / 1
+    const int row = ((warp & 3) << 5) | lane;                   // row of the tile = TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int emb_dim = image->emb_dim, n_kmer = image->n_kmer;
-    unsigned long long* tile_counter =
-        reinterpret_cast<unsigned long long*>(const_cast<long long*>(a.tile_bounds)) + a.n_tiles + 1;
+    const int bar_grp = kBarSe + grp;                           // named barrier of this group (128 threads)
 
-    // ---- slab / tile generator (uniform over the 256 threads of this role) -----------------------------------------------
+    // ---- slab / tile generator (every thread of both groups runs the same sequence) ------------------------------------
+    long long tile = static_cast<long long>(blockIdx.x) - static_cast<long long>(gridDim.x);
     long long tile_s1 = 0, s0 = 0, r0 = 0, s_next = 0;
     int ns = 0, nr = 0, base = 0, slot = -1;
-    uint32_t n_slabs = 0;               // slabs started by this CTA (slot = n % kSlots)
+    uint32_t n_slabs = 0;               // slabs met so far (slot = n % kSlots)
+    uint32_t t_next = 0;                // index of the next MMA tile of this CTA
     bool exhausted = false, have_tile = false;
 
-    auto open_slab = [&](bool stop_marker) {
+    // the slab [s0, s0 + ns) becomes current; `owner`: this group writes its header, the other waits for it
+    auto open_slab = [&](bool owner, bool stop_marker) {
       slot = static_cast<int>(n_slabs % kSlots);
-      mbar_wait(&sm.slab_empty[slot], ((n_slabs / kSlots) & 1u) ^ 1u, kWaitSlabEmpty);
+      const uint32_t use = n_slabs / kSlots;
       ++n_slabs;
-      if (stop_marker) {
-        if (et == 0) sm.meta[slot].stop = 1;
-        return;
-      }
-      if (et <= ns) sm.roff[slot][et] = static_cast<int>(a.read_off[s0 + et] - r0);
-      if (et < ns) {
-        sm.cnt[slot][et] = 0;
-#pragma unroll
-        for (int t = 0; t < kKmerPos; ++t) {
-          int k = a.kmer_idx != nullptr ? a.kmer_idx[(s0 + et) * kKmerPos + t] : 0;
-          sm.kid[slot][et][t] = min(max(k, 0), n_kmer - 1);
+      if (owner) {
+        mbar_wait(&sm.slab_empty[slot], (use & 1u) ^ 1u, kWaitSlabEmpty);
+        if (stop_marker) {
+          if (row == 0) sm.meta[slot].stop = 1;
+          return;
         }
+        if (row <= ns) sm.roff[slot][row] = static_cast<int>(a.read_off[s0 + row] - r0);
+        if (row < ns) {
+          sm.cnt[slot][row] = 0;
+#pragma unroll
+          for (int t = 0; t < kKmerPos; ++t) {
+            int k = a.kmer_idx != nullptr ? a.kmer_idx[(s0 + row) * kKmerPos + t] : 0;
+            sm.kid[slot][row][t] = min(max(k, 0), n_kmer - 1);
+          }
+        }
+        if (row == 0) {
+          SlabMeta m;
+          m.s0 = s0; m.r0 = r0; m.ns = ns; m.nr = nr; m.stop = 0; m.pad = 0;
+          sm.meta[slot] = m;
+        }
+        mbar_arrive(&sm.hdr_ready[slot]);
+        named_bar_sync(bar_grp, kTileM);                        // this group reads the header right away
+      } else if (!stop_marker) {
+        mbar_wait(&sm.hdr_ready[slot], use & 1u, kWaitHdr);
       }
-      if (et == 0) {
-        SlabMeta m;
-        m.s0 = s0; m.r0 = r0; m.ns = ns; m.nr = nr; m.stop = 0; m.pad = 0;
-        sm.meta[slot] = m;
-      }
-      named_bar_sync(kBarSe, kRoleThreads);
     };
 
-    // next MMA tile (advances slices / tiles as needed); slabs without rows are handed to the MC warps directly
+    // next MMA tile of the CTA; `mine`: this group stages it (otherwise only the generator state advances)
     auto next_tile = [&]() -> TileInfo {
       TileInfo ti;
       ti.exists = false; ti.valid = false; ti.last = false; ti.grow = 0; ti.slot = 0; ti.lr = 0; ti.site_l = 0;
+      const bool owner = static_cast<int>(t_next & 1u) == grp;   // whoever stages the next tile opens what comes before it
       while (!exhausted && base >= nr) {                          // current slab exhausted (initially nr = 0)
-        if (!have_tile || s_next >= tile_s1) {                    // next tile of the dynamic counter
-          named_bar_sync(kBarSe, kRoleThreads);                   // everyone has consumed the previous broadcast
-          if (et == 0) sm.next_tile = static_cast<long long>(atomicAdd(tile_counter, 1ull));
-          named_bar_sync(kBarSe, kRoleThreads);
-          const long long tile = sm.next_tile;
+        if (!have_tile || s_next >= tile_s1) {                    // next tile of this CTA
+          tile += gridDim.x;
           if (tile >= a.n_tiles) {
             exhausted = true;
             break;
@@ -377,8 +411,19 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
         r0 = a.read_off[s0];
         nr = static_cast<int>(a.read_off[s0 + ns] - r0);
         base = 0;
-        open_slab(false);
-        if (nr == 0 && half == 0) mbar_arrive(&sm.slab_full[slot]);   // nothing to encode: sites without reads (NaN)
+        if (nr == 0) {
+          // sites without reads have nothing to encode or pool: the owner writes their outputs (NaN, 0) itself.  They take no
+          // slab slot, so every slab in the ring holds at least one MMA tile -- which is what keeps the two groups from
+          // waiting on each other (a slab's last tile is always at least three tiles behind the first tile of the slab
+          // that reuses its slot).
+          if (owner && row < ns) {
+            const size_t o = static_cast<size_t>(s0 + row) * a.site_stride;
+            a.site_prob[o] = __int_as_float(0x7fc00000);
+            a.mod_count[o] = 0;
+          }
+          continue;
+        }
+        open_slab(owner, false);
       }
       if (exhausted) return ti;
       ti.exists = true;
@@ -388,7 +433,8 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
       ti.grow = r0 + ti.lr;
       base += kTileM;
       ti.last = base >= nr;
-      if (ti.valid) {
+      ++t_next;
+      if (owner && ti.valid) {
         int lo = 0, hi = ns;                                       // site of the row: last s with roff[s] <= lr
         while (hi - lo > 1) {
           const int mid = (lo + hi) >> 1;
@@ -399,71 +445,105 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
       return ti;
     };
 
-    // asynchronous prefetch of this thread's 8 inputs of tile `ti` into fbuf[pb][row][8 * half ..] (no register round trip)
-    auto prefetch_inputs = [&](const TileInfo& ti, uint32_t pb) {
-      float* dst = &sm.fbuf[pb][row][8 * half];
+    // asynchronous prefetch of this row's 16 inputs into fbuf[grp][row][0..16) (no register round trip)
+    auto prefetch_inputs = [&](const TileInfo& ti) {
+      float* dst = &sm.fbuf[grp][row][0];
       if (ti.exists && ti.valid) {
         const float* xr = a.feats + ti.grow * kNSig;
-        if (half == 0) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) cp_async4(dst + k, xr + k);
-        } else {
-          cp_async4(dst, xr + 8);
+        for (int k = 0; k < kNSig; ++k) cp_async4(dst + k, xr + k);
 #pragma unroll
-          for (int k = 0; k < 6; ++k) dst[1 + k] = 0.0f;
-          if (emb_dim == 2) {
+        for (int k = kNSig; k < kK1 - 1; ++k) dst[k] = 0.0f;
+        if (emb_dim == 2) {
 #pragma unroll
-            for (int t = 0; t < kKmerPos; ++t) {
-              const float* e = image->emb + 2 * sm.kid[ti.slot][ti.site_l][t];
-              cp_async4(dst + 1 + 2 * t, e);
-              cp_async4(dst + 2 + 2 * t, e + 1);
-            }
-          } else if (emb_dim == 1) {
-#pragma unroll
-            for (int t = 0; t < kKmerPos; ++t) cp_async4(dst + 1 + t, image->emb + sm.kid[ti.slot][ti.site_l][t]);
+          for (int t = 0; t < kKmerPos; ++t) {
+            const float* e = image->emb + 2 * sm.kid[ti.slot][ti.site_l][t];
+            cp_async4(dst + kNSig + 2 * t, e);
+            cp_async4(dst + kNSig + 1 + 2 * t, e + 1);
           }
-          dst[7] = 1.0f;                                         // bias column
+        } else if (emb_dim == 1) {
+#pragma unroll
+          for (int t = 0; t < kKmerPos; ++t) cp_async4(dst + kNSig + t, image->emb + sm.kid[ti.slot][ti.site_l][t]);
         }
+        dst[kK1 - 1] = 1.0f;                                     // bias column
       } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) dst[k] = 0.0f;
+        for (int k = 0; k < kK1; ++k) dst[k] = 0.0f;
       }
       cp_async_commit();
     };
-    // this thread's 8 inputs of the prefetched tile -> RN_tf32 split -> its two k-chunks of X[b]
-    auto stage_x = [&](uint32_t b, uint32_t pb) {
-      cp_async_wait_all();
-      const float4* src = reinterpret_cast<const float4*>(&sm.fbuf[pb][row][8 * half]);
+    // the 16 prefetched inputs of this row -> RN_tf32 split -> the four k-chunks of X[grp]
+    auto stage_x = [&]() {
+      const float4* src = reinterpret_cast<const float4*>(&sm.fbuf[grp][row][0]);
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
+      for (int jj = 0; jj < kK1 / 4; ++jj) {
         const float4 f = src[jj];
         const float4 h = make_float4(rn_tf32(f.x), rn_tf32(f.y), rn_tf32(f.z), rn_tf32(f.w));
         const float4 l = make_float4(f.x - h.x, f.y - h.y, f.z - h.z, f.w - h.w);
-        *reinterpret_cast<float4*>(sm.x[b][0][2 * half + jj][row]) = h;
-        *reinterpret_cast<float4*>(sm.x[b][1][2 * half + jj][row]) = l;     // the hardware truncates lo to TF32
+        *reinterpret_cast<float4*>(sm.x[grp][0][jj][row]) = h;
+        *reinterpret_cast<float4*>(sm.x[grp][1][jj][row]) = l;     // the hardware truncates lo to TF32
       }
     };
+    // advance the generator to this group's next tile (the other group's tile in between only moves the state)
+    auto next_mine = [&]() -> TileInfo {
+      TileInfo ti = next_tile();
+      if (ti.exists && static_cast<int>((t_next - 1u) & 1u) != grp) ti = next_tile();
+      return ti;
+    };
 
-    // Per iteration t: E2 of tile t-2 (frees the single D2 buffer as early as possible) | stage X(t) | prefetch tile t+1.
-    TileInfo ti_s = next_tile();          // tile staged in this iteration
-    TileInfo ti_1, ti_2;                  // tiles t-1, t-2
-    ti_1.exists = false;
-    ti_2.exists = false;
-    prefetch_inputs(ti_s, 0);
+    // Per iteration (this group's k-th tile, t = 2k + grp): stage X(t) | prefetch tile t+2 | E2 of tile t-2.  The MMA issuer needs
+    // X(t) before it needs D2 back (Linear-1 of tile t precedes Linear-2 of tile t-1), and E2 has to wait for Linear-2 of
+    // tile t-2 anyway.
+    TileInfo ti_s = next_mine();          // tile staged in this iteration
+    uint32_t t_s = t_next - 1u;           // its index (meaningful when ti_s.exists)
+    TileInfo ti_e;                        // tile whose E2 is pending (staged one iteration ago)
+    uint32_t t_e = 0;
+    ti_e.exists = false;
+    prefetch_inputs(ti_s);
     bool stop_sent = false;
     PROF_DECL;
-    for (uint32_t t = 0;; ++t) {
-      const uint32_t b = t & 1u;
-      // ---- (1) E2 of tile t-2: this warp's 16 outputs, 8 at a time; the first half finishes the row -------------------------
-      if (ti_2.exists) {
-        const uint32_t u = t - 2, j = u & 1u;
-        const uint32_t d2 = tmem + kColD2 + half * kHalfCols + lane_base;
-        mbar_wait(&sm.d2_full[0], u & 1u, kWaitD2Full);
+    for (;;) {
+      // ---- (2) stage X(t) (or publish the stop) ---------------------------------------------------------------------------
+      TileInfo ti_n;
+      ti_n.exists = false;
+      uint32_t t_n = 0;
+      if (!stop_sent) {
+        if (ti_s.exists) {
+          if (t_s >= 2) mbar_wait(&sm.l1_done[grp], ((t_s - 2) >> 1) & 1u, kWaitL1DoneSe);   // Linear-1 of tile t-2 has consumed X[grp]
+          PROF(0);
+          cp_async_wait_all();
+          PROF(1);
+          if (!(M6A_ABL & 16)) stage_x();
+          if (row == 0) sm.x_ctrl[t_s % kCtrlRing] = 1;
+          PROF(2);
+          if (!(M6A_ABL & 1)) fence_proxy_async();
+          PROF(3);
+          mbar_arrive(&sm.x_full[grp]);
+          PROF(4);
+          // ---- (3) the inputs of this group's next tile travel to shared memory meanwhile ----------------------------------
+          ti_n = next_mine();
+          t_n = t_next - 1u;
+          PROF(5);
+          if (!(M6A_ABL & 16)) prefetch_inputs(ti_n);
+          PROF(6);
+        } else {
+          // no tile left for this group: the group whose turn the next tile index is tells the MMA issuer to stop
+          if (static_cast<int>(t_next & 1u) == grp) {
+            if (row == 0) sm.x_ctrl[t_next % kCtrlRing] = 0;
+            mbar_arrive(&sm.x_full[grp]);
+          }
+          stop_sent = true;
+        }
+      }
+      // ---- (1) E2 of the tile staged one iteration ago: all 32 outputs of this row, 8 at a time ------------------------------
+      if (ti_e.exists) {
+        const uint32_t d2 = tmem + kColD2 + lane_base;
+        mbar_wait(&sm.d2_full[grp], (t_e >> 1) & 1u, kWaitD2Full);
         fence_after();
         PROF(7);
-        float z = 0.0f;
+        float z = sm.b3;
 #pragma unroll
-        for (int o8 = 0; o8 < ((M6A_ABL & 8) ? 0 : kHalfCols); o8 += 8) {
+        for (int o8 = 0; o8 < ((M6A_ABL & 8) ? 0 : kN2); o8 += 8) {
           uint32_t m0[8], c0[8], m1[8], c1[8];
           tmem_ld8(d2 + o8, m0);
           tmem_ld8(d2 + kN2 + o8, c0);
@@ -472,68 +552,38 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
           wait_ld();
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const int o = half * kHalfCols + o8 + k;
             // (main + corr) of each accumulator group, groups added in K order, then the bias: all round-to-nearest float32
             const float h2 = ((__uint_as_float(m0[k]) + __uint_as_float(c0[k])) + (__uint_as_float(m1[k]) + __uint_as_float(c1[k]))) +
-                             sm.b2[o];
-            z = fmaf(sm.w3[o], fmaxf(h2, 0.0f), z);
+                             sm.b2[o8 + k];
+            z = fmaf(sm.w3[o8 + k], fmaxf(h2, 0.0f), z);
           }
         }
         fence_before();
         mbar_arrive(&sm.d2_free[0]);
-        if (half == 1) sm.zpart[j][row] = z;
-        named_bar_sync(kBarSe, kRoleThreads);
         PROF(8);
-        if (half == 0) {
-          z = (z + sm.zpart[j][row]) + sm.b3;
-          const float p = 1.0f / (1.0f + expf(-z));
-          if (ti_2.valid) {
-            a.read_prob[ti_2.grow] = p;
-            if (ti_2.lr < kQCap) sm.q[ti_2.slot][ti_2.lr] = 1.0f - p;
-            if (p >= a.read_threshold) atomicAdd(&sm.cnt[ti_2.slot][ti_2.site_l], 1);
-          }
-          if (ti_2.last) mbar_arrive(&sm.slab_full[ti_2.slot]);
+        const float p = 1.0f / (1.0f + expf(-z));
+        if (ti_e.valid) {
+          a.read_prob[ti_e.grow] = p;
+          if (ti_e.lr < kQCap) sm.q[ti_e.slot][ti_e.lr] = 1.0f - p;
+          if (p >= a.read_threshold) atomicAdd(&sm.cnt[ti_e.slot][ti_e.site_l], 1);
         }
+        if (ti_e.last) mbar_arrive(&sm.slab_full[ti_e.slot]);
         PROF(9);
       }
-      // ---- (2) stage X(t) (or publish the stop) ---------------------------------------------------------------------------
-      TileInfo ti_n;
-      ti_n.exists = false;
-      if (!stop_sent) {
-        if (ti_s.exists) {
-          if (t >= 2) mbar_wait(&sm.l1_done[b], ((t - 2) >> 1) & 1u, kWaitL1DoneSe);   // Linear-1 of tile t-2 has consumed X[b]
-          PROF(0);
-          cp_async_wait_all();
-          PROF(1);
-          if (!(M6A_ABL & 16)) stage_x(b, b);
-          if (et == 0) sm.x_ctrl[t % kCtrlRing] = 1;
-          PROF(2);
-          if (!(M6A_ABL & 1)) fence_proxy_async();
-          PROF(3);
-        } else {
-          if (et == 0) sm.x_ctrl[t % kCtrlRing] = 0;
-          stop_sent = true;
-        }
-        mbar_arrive(&sm.x_full[b]);
-        PROF(4);
-        // ---- (3) the inputs of tile t+1 travel to shared memory meanwhile ----------------------------------------------
-        if (ti_s.exists) {
-          ti_n = next_tile();
-          PROF(5);
-          if (!(M6A_ABL & 16)) prefetch_inputs(ti_n, b ^ 1u);
-        }
-        PROF(6);
-      }
       // ---- (4) rotate -------------------------------------------------------------------------------------------------------
-      ti_2 = ti_1;
-      ti_1 = ti_s;
+      ti_e = ti_s;
+      t_e = t_s;
       ti_s = ti_n;
-      if (stop_sent && !ti_1.exists && !ti_2.exists) break;
+      t_s = t_n;
+      if (stop_sent && !ti_e.exists) break;
     }
-    PROF_STORE(0, et == 0);
-    // tell the MC warps that no slab follows
-    open_slab(true);
-    if (half == 0) mbar_arrive(&sm.slab_full[slot]);
+    PROF_STORE(0, grp == 0 && row == 0);
+    // the stop marker for the MC warps comes from the group whose turn it is
+    {
+      const bool owner = static_cast<int>(t_next & 1u) == grp;
+      open_slab(owner, true);
+      if (owner) mbar_arrive(&sm.slab_full[slot]);
+    }
   } else {
     // ======================================== Monte-Carlo pooling ============================================================
     // A warp takes whole sites of a finished slab (w, w + 15, ...): the blocks of 32 * ipl iterations of one site are the

@@ -26,10 +26,21 @@ __device__ int* g_trap_record = nullptr;   // optional mapped host buffer (m6a_t
 #ifndef M6A_WAIT_SLEEP_NS
 #define M6A_WAIT_SLEEP_NS 0       // > 0: __nanosleep between polls
 #endif
+#ifndef M6A_WAIT_TEST
+#define M6A_WAIT_TEST 0           // 1: mbarrier.test_wait (returns at once) instead of try_wait (suspends inside the memory pipe)
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, int site) {
   uint32_t done = 0;
   for (uint32_t spins = 0; !done; ++spins) {
-#if M6A_WAIT_HINT_NS > 0
+#if M6A_WAIT_TEST
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#elif M6A_WAIT_HINT_NS > 0
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -50,15 +61,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 #if M6A_WAIT_SLEEP_NS > 0
       __nanosleep(M6A_WAIT_SLEEP_NS);
 #endif
-      if (spins > (1u << 24)) {
-        if (g_trap_record != nullptr) {
-          g_trap_record[0] = site;
-          g_trap_record[1] = static_cast<int>(blockIdx.x);
-          g_trap_record[2] = static_cast<int>(threadIdx.x);
-          g_trap_record[3] = static_cast<int>(parity);
+      if (spins >= (1u << 22)) {
+        // every stuck wait leaves its own record (slot = wait site) before the first of them traps a little later
+        if (g_trap_record != nullptr && site >= 0 && site < 16 && spins == (1u << 22)) {
+          int* rec = g_trap_record + 4 * site;
+          rec[0] = site;
+          rec[1] = static_cast<int>(blockIdx.x);
+          rec[2] = static_cast<int>(threadIdx.x);
+          rec[3] = static_cast<int>(parity);
           __threadfence_system();
         }
-        __trap();
+        if (spins > (1u << 25)) __trap();
       }
     }
   }

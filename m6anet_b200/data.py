@@ -321,9 +321,17 @@ class NanopolishDS:
         paths = (C.c_char_p * len(self._paths))(*[os.fsencode(p) for p in self._paths])
         bad = C.c_int64(-1)
         vp = lambda arr: arr.ctypes.data_as(C.c_void_p)
-        rc = _cabi.lib().m6a_ingest_parts(paths, len(self._paths), vp(parts), len(parts), self.num_neighboring_features,
-                                          vp(mean), vp(std), vp(kid), vp(feats), vp(read_ids), vp(kmer_idx), n_threads,
-                                          C.byref(bad))
+        # keys of the sites: the line of every part must name its site's transcript id and position (a stale data.info
+        # raises KeyError in the reference, utils/data_utils.py:185; here M6A_EPARSE)
+        txb = self._tx_bytes[lo:lo + S]
+        lens = np.char.str_len(txb).astype(np.int64) if S else np.zeros(0, np.int64)
+        tx_off = np.zeros(S + 1, dtype=np.int64)
+        np.cumsum(lens, out=tx_off[1:])
+        tx_buf = b"".join(txb.tolist())
+        tx_pos = np.ascontiguousarray(self._pos[lo:lo + S], dtype=np.int64)
+        rc = _cabi.lib().m6a_ingest_parts_keyed(paths, len(self._paths), vp(parts), len(parts), self.num_neighboring_features,
+                                                vp(mean), vp(std), vp(kid), tx_buf, vp(tx_off), vp(tx_pos), vp(feats),
+                                                vp(read_ids), vp(kmer_idx), n_threads, C.byref(bad))
         if rc != 0:
             where = ""
             if bad.value >= 0:

@@ -74,9 +74,10 @@ class MilEngine:
 
     def trap_record(self):
         """Arms (first call) / reads the debug record of the tensor-core kernel's bounded waits: [site, block, thread, parity]."""
-        out = (C.c_int32 * 4)()
+        out = (C.c_int32 * 64)()
         _cabi.check(self._lib.m6a_debug_trap_record(self._handle, out), "m6a_debug_trap_record")
-        return list(out)
+        v = list(out)
+        return [v[4 * i:4 * i + 4] for i in range(16) if v[4 * i] != 0]
 
     def set_tile_reads(self, tile_reads: int = 0):
         """Feature rows per tile (64..4096); 0 = automatic (a multiple of the site depth near 1000 rows)."""

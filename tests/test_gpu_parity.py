@@ -322,7 +322,7 @@ def test_headline_size_config3_sampled_sites():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     eng = engine("HCT116_RNA002")
-    feats, off, kmer = bench.synth_shard(0, 1_000_000, 50, 1)
+    feats, off, kmer = bench.synth_shard(0, 1_000_000, 50, 1, total_sites=1_000_000)
     rp, sp, mc = eng.infer_host(feats, off, kmer, 1000, seed=0, read_threshold=0.033379376)
 
     class A:

@@ -1,5 +1,5 @@
 #!/bin/bash
-for v in "" _c2 _hi _hic2; do
+for v in "" _tw0 _tw100 _tw400; do
   echo "== lib$v"
   M6A_LIB=$PWD/m6anet_b200/libm6anet_b200$v.so timeout 300 python tools/gpu_quick_tc2.py --no-parity --time --only-big --only-tc 2>&1 | grep -E '"encoder"|rror' | cut -c1-100
 done

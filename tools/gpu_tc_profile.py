@@ -31,8 +31,8 @@ assert L.m6a_debug_tc_profile(out) == 0
 v = list(out)
 tiles = S * n / 128 / 148
 roles = [
-    ("staging + E2 thread 0", 0, ["wait l1_done(t-2)", "cp.async wait", "split + STS", "fence.proxy.async", "arrive x_full", "next_tile", "prefetch issue",
-                                   "wait d2_full", "E2 ld + z + bar", "E2 sigmoid + outputs"]),
+    ("staging + E2 group 0 row 0 (every second tile)", 0, ["wait l1_done(t-2)", "cp.async wait", "split + STS", "fence.proxy.async", "arrive x_full", "next_tile", "prefetch issue",
+                                   "wait d2_full", "E2 TMEM read + logits", "E2 sigmoid + outputs"]),
     ("MMA issuer", 10, ["wait x_full", "L1 issue+commit", "wait d2_free", "wait a_full (5x)", "L2 issue+commit (5x)"]),
     ("E1 thread 0", 30, ["wait l1_done", "tmem_ld+wait (5x)", "relu/split (5x)", "wait a_free (5x)", "tmem_st+wait+arrive (5x)"]),
     ("MC warp 0", 20, ["wait slab_full", "sites of the slab", "-", "report"]),
