@@ -54,7 +54,10 @@ constexpr int kMcWarps = 15;                 // warps 0, 2, 3, 20..31
 #define M6A_MC_CHAINS 2     // measured on B200 (1 M x 50 x 1000): 2 chains 12.84 ms, 4 chains 13.34 ms
 #endif
 constexpr int kMcChains = M6A_MC_CHAINS;     // blocks of a site a Monte-Carlo warp interleaves
-constexpr int kSlots = 3;                    // slab slots in shared memory (q table, offsets, counters)
+#ifndef M6A_TC_SLOTS
+#define M6A_TC_SLOTS 3
+#endif
+constexpr int kSlots = M6A_TC_SLOTS;                    // slab slots in shared memory (q table, offsets, counters)
 constexpr int kSlabSites = kSitesPerTileMax; // 64
 constexpr int kTmemCols = 512;
 constexpr uint32_t kColD1 = 0, kColALo = 2 * kN1, kColD2 = 2 * kN1 + 2 * kChunk;   // 0 | 320 | 384
@@ -84,7 +87,8 @@ struct alignas(128) TcSmem {
   float w1lo[kK1 / 4][kN1][4];                  // 10 KB
   float w2s[kN1 / 4][2 * kN2][4];               // 40 KB   B of Linear-2 (rows 0..31 hi, 32..63 lo)
   float x[2][2][kK1 / 4][kTileM][4];            // 32 KB   A of Linear-1: [buffer][hi, lo][k-chunk][row][4]
-  float fbuf[2][kTileM][kK1];                   // 16 KB   prefetched inputs of the next tile (cp.async), [x(9) | emb | 1]
+  float fbuf[2][kK1][kTileM];                   // 16 KB   prefetched inputs of a group's next tile (cp.async), input-major:
+                                                //         [x(9) | emb | 1][row] -- lanes = rows, no bank conflicts
   float q[kSlots][kQCap];                       // 48 KB   q = 1 - p of a slab
   float b2[kN2];
   float w3[kN2];
@@ -445,39 +449,40 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
       return ti;
     };
 
-    // asynchronous prefetch of this row's 16 inputs into fbuf[grp][row][0..16) (no register round trip)
+    // asynchronous prefetch of this row's 16 inputs into fbuf[grp][0..16)[row] (no register round trip)
     auto prefetch_inputs = [&](const TileInfo& ti) {
-      float* dst = &sm.fbuf[grp][row][0];
+      float* dst = &sm.fbuf[grp][0][row];                        // input k lives at dst[k * kTileM]
       if (ti.exists && ti.valid) {
         const float* xr = a.feats + ti.grow * kNSig;
 #pragma unroll
-        for (int k = 0; k < kNSig; ++k) cp_async4(dst + k, xr + k);
+        for (int k = 0; k < kNSig; ++k) cp_async4(dst + k * kTileM, xr + k);
 #pragma unroll
-        for (int k = kNSig; k < kK1 - 1; ++k) dst[k] = 0.0f;
+        for (int k = kNSig; k < kK1 - 1; ++k) dst[k * kTileM] = 0.0f;
         if (emb_dim == 2) {
 #pragma unroll
           for (int t = 0; t < kKmerPos; ++t) {
             const float* e = image->emb + 2 * sm.kid[ti.slot][ti.site_l][t];
-            cp_async4(dst + kNSig + 2 * t, e);
-            cp_async4(dst + kNSig + 1 + 2 * t, e + 1);
+            cp_async4(dst + (kNSig + 2 * t) * kTileM, e);
+            cp_async4(dst + (kNSig + 1 + 2 * t) * kTileM, e + 1);
           }
         } else if (emb_dim == 1) {
 #pragma unroll
-          for (int t = 0; t < kKmerPos; ++t) cp_async4(dst + kNSig + t, image->emb + sm.kid[ti.slot][ti.site_l][t]);
+          for (int t = 0; t < kKmerPos; ++t) cp_async4(dst + (kNSig + t) * kTileM, image->emb + sm.kid[ti.slot][ti.site_l][t]);
         }
-        dst[kK1 - 1] = 1.0f;                                     // bias column
+        dst[(kK1 - 1) * kTileM] = 1.0f;                          // bias column
       } else {
 #pragma unroll
-        for (int k = 0; k < kK1; ++k) dst[k] = 0.0f;
+        for (int k = 0; k < kK1; ++k) dst[k * kTileM] = 0.0f;
       }
       cp_async_commit();
     };
     // the 16 prefetched inputs of this row -> RN_tf32 split -> the four k-chunks of X[grp]
     auto stage_x = [&]() {
-      const float4* src = reinterpret_cast<const float4*>(&sm.fbuf[grp][row][0]);
+      const float* src = &sm.fbuf[grp][0][row];
 #pragma unroll
       for (int jj = 0; jj < kK1 / 4; ++jj) {
-        const float4 f = src[jj];
+        const float4 f = make_float4(src[(4 * jj) * kTileM], src[(4 * jj + 1) * kTileM], src[(4 * jj + 2) * kTileM],
+                                     src[(4 * jj + 3) * kTileM]);
         const float4 h = make_float4(rn_tf32(f.x), rn_tf32(f.y), rn_tf32(f.z), rn_tf32(f.w));
         const float4 l = make_float4(f.x - h.x, f.y - h.y, f.z - h.z, f.w - h.w);
         *reinterpret_cast<float4*>(sm.x[grp][0][jj][row]) = h;

@@ -24,55 +24,54 @@ __device__ int* g_trap_record = nullptr;   // optional mapped host buffer (m6a_t
 #define M6A_WAIT_HINT_NS 0        // > 0: mbarrier.try_wait with this suspend-time hint (ns)
 #endif
 #ifndef M6A_WAIT_SLEEP_NS
-#define M6A_WAIT_SLEEP_NS 0       // > 0: __nanosleep between polls
+#define M6A_WAIT_SLEEP_NS 0       // > 0: __nanosleep between groups of polls
 #endif
-#ifndef M6A_WAIT_TEST
-#define M6A_WAIT_TEST 0           // 1: mbarrier.test_wait (returns at once) instead of try_wait (suspends inside the memory pipe)
-#endif
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, int site) {
-  uint32_t done = 0;
-  for (uint32_t spins = 0; !done; ++spins) {
-#if M6A_WAIT_TEST
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-#elif M6A_WAIT_HINT_NS > 0
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(M6A_WAIT_HINT_NS))
-        : "memory");
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_addr, uint32_t parity) {
+  uint32_t done;
+#if M6A_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar_addr), "r"(parity), "r"(static_cast<uint32_t>(M6A_WAIT_HINT_NS))
+      : "memory");
 #else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
 #endif
-    if (!done) {
+  return done;
+}
+// Bounded wait.  ncu of the first version (one poll, one counter update and one limit test per trip) showed a third of all
+// issued instructions in this loop, so the polls come four to a trip and the bookkeeping once per trip.
+__device__ __noinline__ void mbar_wait_timeout(int site, uint32_t parity) {
+  if (g_trap_record != nullptr && site >= 0 && site < 16) {
+    int* rec = g_trap_record + 4 * site;
+    rec[0] = site;
+    rec[1] = static_cast<int>(blockIdx.x);
+    rec[2] = static_cast<int>(threadIdx.x);
+    rec[3] = static_cast<int>(parity);
+    __threadfence_system();
+  }
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, int site) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(addr, parity)) return;
+  for (uint32_t trips = 0;; ++trips) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (mbar_try_wait(addr, parity)) return;
 #if M6A_WAIT_SLEEP_NS > 0
-      __nanosleep(M6A_WAIT_SLEEP_NS);
+    __nanosleep(M6A_WAIT_SLEEP_NS);
 #endif
-      if (spins >= (1u << 22)) {
-        // every stuck wait leaves its own record (slot = wait site) before the first of them traps a little later
-        if (g_trap_record != nullptr && site >= 0 && site < 16 && spins == (1u << 22)) {
-          int* rec = g_trap_record + 4 * site;
-          rec[0] = site;
-          rec[1] = static_cast<int>(blockIdx.x);
-          rec[2] = static_cast<int>(threadIdx.x);
-          rec[3] = static_cast<int>(parity);
-          __threadfence_system();
-        }
-        if (spins > (1u << 25)) __trap();
-      }
+    if (trips >= (1u << 21)) {                       // ~1 s: every stuck wait leaves its record, the first one traps later
+      if (trips == (1u << 21)) mbar_wait_timeout(site, parity);
+      if (trips > (1u << 24)) __trap();
     }
   }
 }

@@ -154,6 +154,48 @@ def time_stock_run_inference(pretrained, feats, read_off, kmer_idx, n_iters, n_p
     return dict(sites_per_s=rows / dt if dt > 0 else 0.0, seconds=dt, sites_written=rows, sites_given=len(ds), cores=n_procs)
 
 
+class _ResidentBags:
+    """In-memory stand-in for the reference's evaluation datasets: __getitem__ draws `min_reads` reads of the site without
+    replacement exactly like NanopolishDS in 'Val' / 'Test' mode (utils/data_utils.py:213-214) and returns
+    (features, kmer, label); batches are formed by the stock train_collate."""
+
+    def __init__(self, feats, read_off, kmer_idx, labels, min_reads=20):
+        self.torch = _ref()["torch"]
+        self.feats, self.off, self.kmer = feats, np.asarray(read_off, np.int64), np.asarray(kmer_idx, np.int64)
+        self.labels, self.min_reads = labels, min_reads
+
+    def __len__(self):
+        return len(self.off) - 1
+
+    def __getitem__(self, i):
+        a, b = int(self.off[i]), int(self.off[i + 1])
+        f = self.feats[a:b]
+        f = f[np.random.choice(len(f), self.min_reads, replace=False), :]             # utils/data_utils.py:214
+        x = self.torch.Tensor(np.ascontiguousarray(f))
+        k = self.torch.LongTensor(np.repeat(self.kmer[i][None, :], len(f), axis=0))
+        return x, k, self.labels[i]
+
+
+def time_stock_validate(pretrained, feats, read_off, kmer_idx, n_iterations, n_procs, batch_size=512):
+    """The reference's validate() itself (utils/training_utils.py:213-268): n_iterations passes over the sites, each pass a
+    fresh bag of 20 reads per site through MILModel.forward; DataLoader with the stock train_collate, resident inputs."""
+    R = _ref()
+    from torch.utils.data import DataLoader
+    from m6anet.utils.training_utils import validate
+    torch = R["torch"]
+    torch.set_num_threads(n_procs)
+    model, _ = stock_model(pretrained)
+    n_sites = len(read_off) - 1
+    labels = (np.arange(n_sites) % 2).astype(np.int64)
+    ds = _ResidentBags(feats, read_off, kmer_idx, labels)
+    dl = DataLoader(ds, num_workers=0, collate_fn=R["data_utils"].train_collate, batch_size=batch_size, shuffle=False)
+    t0 = time.perf_counter()
+    res = validate(model, dl, "cpu", torch.nn.BCELoss(), n_iterations)
+    dt = time.perf_counter() - t0
+    return dict(sites_per_s=n_sites / dt, seconds=dt, n_sites=n_sites, n_iterations=n_iterations, cores=n_procs,
+                roc_auc=float(res["roc_auc"]))
+
+
 if __name__ == "__main__":   # python -m oracle.ref_arm : quick self-check on synthetic sites
     rng = np.random.default_rng(0)
     S, n = int(os.environ.get('REF_ARM_SITES', '512')), 50

@@ -139,6 +139,9 @@ if "--time" in sys.argv:
         sizes.append((1_000_000, 50))
     if "--only-big" in sys.argv:
         sizes = [(1_000_000, 50)]
+    for arg in sys.argv:
+        if arg.startswith("--sizes="):          # --sizes=1000000:32,1000000:64
+            sizes = [tuple(int(v) for v in x.split(":")) for x in arg.split("=", 1)[1].split(",")]
     encs = ("tc",) if "--only-tc" in sys.argv else ("tc", "ffma")
     eng = engine_for("HCT116_RNA002")
     eng.trap_record()
