@@ -103,8 +103,10 @@ const char *m6a_strerror(int status);
 int m6a_device_count(int32_t *count);
 int m6a_set_device(int32_t device);
 
-/* Packs the weights into the kernel's shared-memory image and uploads it to the current CUDA
- * device (synchronous).  The model may be used from any stream of that device. */
+/* Packs the weights into the two images the kernels consume -- the pair-interleaved image of the CUDA-core kernel (passed by
+ * value as a __grid_constant__ kernel parameter) and the RN_tf32 hi/lo split UMMA operands of the tensor-core kernel (copied
+ * to shared memory once per CTA) -- and uploads them to the current CUDA device (synchronous).  The model may be used from any
+ * stream of that device. */
 int m6a_model_create(const m6a_weights_t *w, m6a_model_t **out);
 int m6a_model_destroy(m6a_model_t *model);
 /* Selects the read-encoder implementation of this model (M6A_ENCODER_*); the environment variable M6A_ENCODER=ffma|tc

@@ -204,7 +204,7 @@ extern "C" int m6a_model_create(const m6a_weights_t* w, m6a_model_t** out) {
 
 extern "C" int m6a_model_set_tile_reads(m6a_model_t* model, int32_t tile_reads) {
   if (!model) return M6A_EINVAL;
-  if (tile_reads != 0 && (tile_reads < 64 || tile_reads > kQCap)) return M6A_EINVAL;
+  if (tile_reads != 0 && (tile_reads < 64 || tile_reads > kQCap)) return M6A_EINVAL;   // (both kernels accept 64..4096)
   model->tile_reads = tile_reads;
   return M6A_OK;
 }
@@ -290,15 +290,15 @@ static int auto_tile_reads(long long n_sites, long long total_reads, int n_sms) 
 }
 
 // Rows per tile for the tensor-core kernel: slabs are slices of <= 64 sites, encoded 128 rows at a time, so a tile of
-// 64 sites' worth of rows (a multiple of 128 for every even site depth) wastes no MMA rows; <= 4096 rows (q table).
+// 64 sites' worth of rows (a multiple of 128 for every even site depth) wastes no MMA rows; <= 6144 rows (q table).
 static int auto_tile_reads_tc(long long n_sites, long long total_reads) {
   long long base = 2048;
   if (n_sites > 0 && total_reads % n_sites == 0) {
     const long long depth = total_reads / n_sites;
-    if (depth >= 1 && depth * kSitesPerTileMax <= kQCap) base = depth * kSitesPerTileMax;
-    else if (depth >= 1 && depth <= kQCap) base = (kQCap / depth) * depth;
+    if (depth >= 1 && depth * kSitesPerTileMax <= kTcQCap) base = depth * kSitesPerTileMax;
+    else if (depth >= 1 && depth <= kTcQCap) base = (kTcQCap / depth) * depth;
   }
-  return static_cast<int>(std::max<long long>(64, std::min<long long>(base, kQCap)));
+  return static_cast<int>(std::max<long long>(64, std::min<long long>(base, kTcQCap)));
 }
 
 static int infer_device_impl(const m6a_model_t* model, int tile_reads, const float* feats, const int64_t* read_off,

@@ -44,6 +44,7 @@ constexpr int kChunkReads = kThreads * kReadsPerThread;  // feature rows staged 
 constexpr int kSitesPerTileMax = M6A_GMAX;
 constexpr int kQCap = M6A_QCAP;         // q = 1-p entries kept in shared memory per tile
 constexpr int kCStride = kH1Max;        // even (float2 loads); 152 mod 32 = 24 keeps neighbouring site rows on distinct banks
+constexpr int kTcQCap = 6144;           // q entries of a slab slot of the tensor-core kernel (m6a_kernel_tc.cu)
 constexpr int kMcMaxBlocks = 64;        // == kMaxBlocks in m6a_rng.cuh: Monte-Carlo partial sums per site
 constexpr int kMcMinItersPerLane = 8;
 

@@ -50,6 +50,12 @@ constexpr int kSeWarp0 = 12;
 constexpr int kRoleWarps = 8;
 constexpr int kRoleThreads = kRoleWarps * 32;   // 256
 constexpr int kMcWarps = 15;                 // warps 0, 2, 3, 20..31
+// 1: Monte-Carlo pooling with lanes = sites (site-interleaved q table, conflict-free loads) where the slab fits.  Measured on
+// B200 (1 M x 50 x 1000): 11.94 ms with it, 11.17 ms without -- the bank conflicts of the row-order table are not what
+// limits the pooling; kept as an experiment (parity-checked, bit-identical site sums).
+#ifndef M6A_TC_LANES_SITES
+#define M6A_TC_LANES_SITES 0
+#endif
 #ifndef M6A_MC_CHAINS
 #define M6A_MC_CHAINS 2     // measured on B200 (1 M x 50 x 1000): 2 chains 12.84 ms, 4 chains 13.34 ms
 #endif
@@ -74,11 +80,17 @@ constexpr uint32_t kLboX = kTileM * 16, kStepX = 2 * kLboX;
 constexpr uint32_t kLboW1 = kN1 * 16, kStepW1 = 2 * kLboW1;
 constexpr uint32_t kLboW2 = 2 * kN2 * 16, kStepW2 = 2 * kLboW2;
 
+constexpr int kQCapT = kTcQCap;              // q entries of a slab slot (24 KB)
+constexpr int kLaneBlocksMax = 4;            // lanes = sites pooling: blocks of iterations per site it covers (n_iters <= 1024)
+constexpr int kOctets = 8;                   // a block's 32 lane streams in 8 groups of 4 = the b_k level of the butterfly sum
+
 struct SlabMeta {
   long long s0;      // first site of the slab (shard-local)
   long long r0;      // first feature row
   int ns, nr;        // sites, rows
   int stop;          // 1: no more slabs for this CTA
+  int max_n;         // most reads of a site of the slab
+  int mode;          // 1: q stored site-interleaved (lanes = sites pooling), 0: q in row order, -1: q not in shared memory
   int pad;
 };
 
@@ -89,7 +101,10 @@ struct alignas(128) TcSmem {
   float x[2][2][kK1 / 4][kTileM][4];            // 32 KB   A of Linear-1: [buffer][hi, lo][k-chunk][row][4]
   float fbuf[2][kK1][kTileM];                   // 16 KB   prefetched inputs of a group's next tile (cp.async), input-major:
                                                 //         [x(9) | emb | 1][row] -- lanes = rows, no bank conflicts
-  float q[kSlots][kQCap];                       // 48 KB   q = 1 - p of a slab
+  float q[kSlots][kQCapT];                      // 72 KB   q = 1 - p of a slab (row order, or [group][entry][32 sites])
+#if M6A_TC_LANES_SITES
+  float part[kSlots][2][kLaneBlocksMax][kOctets][32];   // 24 KB  lanes = sites pooling: b_k partial sums per (group, block)
+#endif
   float b2[kN2];
   float w3[kN2];
   float b3;
@@ -109,6 +124,7 @@ struct alignas(128) TcSmem {
                                                 // take turns
   alignas(8) unsigned long long d2_free[1];     // E2 (256)      -> MMA : D2 read out
   int done[kSlots];                             // MC warps finished with the slab of a slot
+  int maxn_scratch[2][4];
   alignas(8) unsigned long long slab_full[kSlots];   // E2 (128) -> MC
   alignas(8) unsigned long long slab_empty[kSlots];  // MC (1)   -> staging
   alignas(8) unsigned long long hdr_ready[kSlots];   // staging group that opened the slab (128) -> the other group
@@ -380,13 +396,24 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
             sm.kid[slot][row][t] = min(max(k, 0), n_kmer - 1);
           }
         }
+        // most reads of a site -> layout of the slab's q table: site-interleaved when it fits (lanes = sites pooling)
+        int my_n = row < ns ? static_cast<int>(a.read_off[s0 + row + 1] - a.read_off[s0 + row]) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_n = max(my_n, __shfl_xor_sync(0xffffffffu, my_n, o));
+        if (lane == 0) sm.maxn_scratch[grp][warp & 3] = my_n;
+        named_bar_sync(bar_grp, kTileM);
         if (row == 0) {
           SlabMeta m;
           m.s0 = s0; m.r0 = r0; m.ns = ns; m.nr = nr; m.stop = 0; m.pad = 0;
+          m.max_n = max(max(sm.maxn_scratch[grp][0], sm.maxn_scratch[grp][1]), max(sm.maxn_scratch[grp][2], sm.maxn_scratch[grp][3]));
+          const int n_groups = (ns + 31) >> 5;
+          const bool lanes_ok = M6A_TC_LANES_SITES && n_blocks <= kLaneBlocksMax && m.max_n >= 1 &&
+                                m.max_n <= static_cast<int>(kPairedMaxReads) && n_groups * 32 * m.max_n <= kQCapT;
+          m.mode = lanes_ok ? 1 : (nr <= kQCapT ? 0 : -1);
           sm.meta[slot] = m;
         }
-        mbar_arrive(&sm.hdr_ready[slot]);
         named_bar_sync(bar_grp, kTileM);                        // this group reads the header right away
+        mbar_arrive(&sm.hdr_ready[slot]);
       } else if (!stop_marker) {
         mbar_wait(&sm.hdr_ready[slot], use & 1u, kWaitHdr);
       }
@@ -569,7 +596,15 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
         const float p = 1.0f / (1.0f + expf(-z));
         if (ti_e.valid) {
           a.read_prob[ti_e.grow] = p;
-          if (ti_e.lr < kQCap) sm.q[ti_e.slot][ti_e.lr] = 1.0f - p;
+          {
+            const int mode = sm.meta[ti_e.slot].mode;
+            if (mode == 1) {            // [group][entry][32 sites]
+              const int entry = ti_e.lr - sm.roff[ti_e.slot][ti_e.site_l];
+              sm.q[ti_e.slot][((ti_e.site_l >> 5) * sm.meta[ti_e.slot].max_n + entry) * 32 + (ti_e.site_l & 31)] = 1.0f - p;
+            } else if (mode == 0) {
+              sm.q[ti_e.slot][ti_e.lr] = 1.0f - p;
+            }
+          }
           if (p >= a.read_threshold) atomicAdd(&sm.cnt[ti_e.slot][ti_e.site_l], 1);
         }
         if (ti_e.last) mbar_arrive(&sm.slab_full[ti_e.slot]);
@@ -609,9 +644,117 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
       const SlabMeta m = sm.meta[slot];
       if (m.stop) break;
       const int ns = m.ns;
-      const bool q_in_smem = m.nr <= kQCap;
+      const bool q_in_smem = m.mode == 0;
       const int* roff = sm.roff[slot];
       const float* q = sm.q[slot];
+#if M6A_TC_LANES_SITES
+      if (m.mode == 1 && !(M6A_ABL & 32)) {
+        // ---- lanes = sites: hardware lane L pools site 32 g + L; an item = (group g, block b, octet k) = the four lane
+        // streams {k, k+16, k+8, k+24} of block b, i.e. the partial sum b_k of the butterfly sum of m6a_mc.cuh, so the final
+        // result is the same float32 expression as everywhere else.  Every lane of a warp reads its own column of the
+        // site-interleaved q table: one shared-memory wavefront per load whatever the indices are.
+        const int n_groups = (ns + 31) >> 5;
+        const int items = n_groups * n_blocks * kOctets;
+        for (int item = mcw; item < items; item += kMcWarps) {
+          const int g = item / (n_blocks * kOctets), rem = item - g * (n_blocks * kOctets);
+          const int b = rem / kOctets, k = rem - b * kOctets;
+          const int sl = 32 * g + lane;
+          const bool live = sl < ns;
+          const int nreads = live ? roff[sl + 1] - roff[sl] : 0;
+          const uint32_t n = nreads > 0 ? static_cast<uint32_t>(nreads) : 1u;        // idle lanes read entry 0 of their column
+          const unsigned long long site_id = static_cast<unsigned long long>(a.site_id_base + m.s0 + (live ? sl : 0));
+          const uint32_t qaddr = mc_smem_u32(q + static_cast<size_t>(g) * m.max_n * 32 + lane);
+          float v[4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {                // (k, k+16) then (k+8, k+24): two chains at a time
+            const int vl0 = k + 8 * h, vl1 = vl0 + 16;
+            Mwc64x g0, g1;
+            g0.seed(static_cast<uint32_t>(vl0), static_cast<uint32_t>(b), site_id, a.seed);
+            g1.seed(static_cast<uint32_t>(vl1), static_cast<uint32_t>(b), site_id, a.seed);
+            const long long it0 = static_cast<long long>(b) * ipl * 32;
+            const long long l0 = (static_cast<long long>(a.n_iters) - (it0 + vl0) + 31) / 32;
+            const long long l1 = (static_cast<long long>(a.n_iters) - (it0 + vl1) + 31) / 32;
+            const int r0_ = static_cast<int>(l0 < 0 ? 0 : (l0 > ipl ? ipl : l0)), r1_ = static_cast<int>(l1 < 0 ? 0 : (l1 > ipl ? ipl : l1));
+            float s0_ = 0.0f, s1_ = 0.0f;
+            const int rc = min(r0_, r1_);
+            for (int r = 0; r < rc; ++r) {
+              float p0 = 1.0f, p1 = 1.0f;
+#pragma unroll
+              for (int s = 0; s < NS / 2; ++s) {
+                uint32_t i1, i2, j1, j2;
+                g0.next_pair(n, i1, i2);
+                g1.next_pair(n, j1, j2);
+                p0 *= lds_f32(qaddr + (i1 << 7));
+                p1 *= lds_f32(qaddr + (j1 << 7));
+                p0 *= lds_f32(qaddr + (i2 << 7));
+                p1 *= lds_f32(qaddr + (j2 << 7));
+              }
+              s0_ += 1.0f - p0;
+              s1_ += 1.0f - p1;
+            }
+            for (int r = rc; r < r0_; ++r) {
+              float p0 = 1.0f;
+#pragma unroll
+              for (int s = 0; s < NS / 2; ++s) {
+                uint32_t i1, i2;
+                g0.next_pair(n, i1, i2);
+                p0 *= lds_f32(qaddr + (i1 << 7));
+                p0 *= lds_f32(qaddr + (i2 << 7));
+              }
+              s0_ += 1.0f - p0;
+            }
+            for (int r = rc; r < r1_; ++r) {
+              float p1 = 1.0f;
+#pragma unroll
+              for (int s = 0; s < NS / 2; ++s) {
+                uint32_t j1, j2;
+                g1.next_pair(n, j1, j2);
+                p1 *= lds_f32(qaddr + (j1 << 7));
+                p1 *= lds_f32(qaddr + (j2 << 7));
+              }
+              s1_ += 1.0f - p1;
+            }
+            v[2 * h] = s0_;
+            v[2 * h + 1] = s1_;
+          }
+          sm.part[slot][g][b][k][lane] = (v[0] + v[1]) + (v[2] + v[3]);       // b_k = (v_k + v_k+16) + (v_k+8 + v_k+24)
+        }
+        PROF(1);
+        __syncwarp();
+        bool last = false;
+        if (lane == 0) {
+          __threadfence_block();
+          last = atomicAdd(&sm.done[slot], 1) == kMcWarps - 1;
+        }
+        last = __shfl_sync(0xffffffffu, last ? 1 : 0, 0) != 0;
+        if (last) {                      // every item of the slab is in: finish the butterfly sums, write the sites
+          __threadfence_block();
+          for (int g = 0; g < n_groups; ++g) {
+            const int sl = 32 * g + lane;
+            if (sl < ns) {
+              const int nreads = roff[sl + 1] - roff[sl];
+              float total = 0.0f;
+              for (int b = 0; b < n_blocks; ++b) {
+                const float (&bk)[kOctets][32] = sm.part[slot][g][b];
+                const float c0 = bk[0][lane] + bk[4][lane], c1 = bk[1][lane] + bk[5][lane];
+                const float c2 = bk[2][lane] + bk[6][lane], c3 = bk[3][lane] + bk[7][lane];
+                total += (c0 + c2) + (c1 + c3);
+              }
+              const size_t o = static_cast<size_t>(m.s0 + sl) * a.site_stride;
+              a.site_prob[o] = nreads > 0 ? total / n_iters_f : __int_as_float(0x7fc00000);
+              a.mod_count[o] = sm.cnt[slot][sl];
+            }
+          }
+          __syncwarp();
+          if (lane == 0) {
+            sm.done[slot] = 0;
+            mbar_arrive(&sm.slab_empty[slot]);
+          }
+        }
+        PROF(3);
+        continue;
+      }
+#endif
 
       auto lane_rounds = [&](int blk_) {
         const long long it0 = static_cast<long long>(blk_) * ipl * 32 + lane;

@@ -581,3 +581,46 @@ def test_append_file_concatenates_shards(tmp_path):
             append_file(out, str(tmp_path / "shard"))
             out.write(b"tail")
         assert out_path.read_bytes() == b"header\n" + blob + blob + b"tail"
+
+
+def test_m6anet_console_entry():
+    """`m6anet inference ...` of the reference (m6anet/__init__.py:11-30, setup.py:47-54) is served by bin/m6anet and by the
+    `m6anet` script of pyproject.toml; the sub-commands outside the hot path say so instead of failing obscurely."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "bin", "m6anet")
+    r = subprocess.run([sys.executable, exe, "--version"], capture_output=True, text=True)
+    assert r.returncode == 0 and "m6anet-b200" in r.stdout
+    r = subprocess.run([sys.executable, exe, "inference", "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--pretrained_model" in r.stdout and "--num_iterations" in r.stdout
+    r = subprocess.run([sys.executable, exe, "dataprep"], capture_output=True, text=True)
+    assert r.returncode != 0 and "outside the m6anet_b200 scope" in r.stderr
+    text = open(os.path.join(root, "pyproject.toml")).read()
+    assert 'm6anet = "m6anet_b200.__main__:main"' in text
+
+
+def test_native_ingest_checks_keys_against_data_info(tmp_path):
+    """A data.info whose byte ranges point at ANOTHER site's line (same read count) must not be scored under the wrong
+    transcript / position: the reference indexes json.loads(line)[tx_id][str(tx_pos)] and raises KeyError
+    (utils/data_utils.py:185); here the native parser refuses the part (M6A_EPARSE)."""
+    from m6anet_b200 import _cabi
+    from m6anet_b200.constants import PRETRAINED_CONFIGS
+    from m6anet_b200.data import NanopolishDS
+    sys_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+    import sys
+    sys.path.insert(0, sys_path)
+    from make_synthetic_dataset import write_dataset
+    d = tmp_path / "d"
+    write_dataset(str(d), 6, 20, seed=3)
+    norm = PRETRAINED_CONFIGS["HCT116_RNA002"][2]
+    assert len(NanopolishDS(str(d), 20, norm, mode="Inference").load_sites(0, 6).read_off) == 7       # intact: fine
+    lines = open(d / "data.info").read().splitlines()
+    a, b = lines[2].split(","), lines[3].split(",")
+    a[2:4], b[2:4] = b[2:4], a[2:4]                                  # swap the byte ranges of sites 1 and 2
+    lines[2], lines[3] = ",".join(a), ",".join(b)
+    open(d / "data.info", "w").write("\n".join(lines) + "\n")
+    ds = NanopolishDS(str(d), 20, norm, mode="Inference")
+    with pytest.raises(_cabi.M6AError) as e:
+        ds.load_sites(0, 6)
+    assert e.value.status == -6                                       # M6A_EPARSE
