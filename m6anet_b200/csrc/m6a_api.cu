@@ -291,14 +291,25 @@ static int auto_tile_reads(long long n_sites, long long total_reads, int n_sms) 
 
 // Rows per tile for the tensor-core kernel: slabs are slices of <= 64 sites, encoded 128 rows at a time, so a tile of
 // 64 sites' worth of rows (a multiple of 128 for every even site depth) wastes no MMA rows; <= 6144 rows (q table).
-static int auto_tile_reads_tc(long long n_sites, long long total_reads) {
+// Tiles are dealt round-robin to one CTA per SM: when the job is only a few rounds long (one shard of an 8-GPU run: 13.2
+// rounds of 3200 rows), the tile is shrunk to total / (ceil(rounds) * SMs), rounded up to whole MMA tiles, so that the last
+// round is as full as the others (14 rounds of 3072 rows instead of 14 of 3200).
+static int auto_tile_reads_tc(long long n_sites, long long total_reads, int n_sms) {
   long long base = 2048;
   if (n_sites > 0 && total_reads % n_sites == 0) {
     const long long depth = total_reads / n_sites;
     if (depth >= 1 && depth * kSitesPerTileMax <= kTcQCap) base = depth * kSitesPerTileMax;
     else if (depth >= 1 && depth <= kTcQCap) base = (kTcQCap / depth) * depth;
   }
-  return static_cast<int>(std::max<long long>(64, std::min<long long>(base, kTcQCap)));
+  base = std::max<long long>(64, std::min<long long>(base, kTcQCap));
+  const long long grid = std::max(1, n_sms);
+  const long long rounds = (total_reads + base * grid - 1) / (base * grid);
+  if (rounds >= 1 && rounds < 64) {
+    long long t = (total_reads + rounds * grid - 1) / (rounds * grid);
+    t = (t + tcx::kTileM - 1) / tcx::kTileM * tcx::kTileM;
+    if (t >= 256 && t < base) base = t;
+  }
+  return static_cast<int>(base);
 }
 
 static int infer_device_impl(const m6a_model_t* model, int tile_reads, const float* feats, const int64_t* read_off,
@@ -332,7 +343,7 @@ static int infer_device_impl(const m6a_model_t* model, int tile_reads, const flo
   const bool use_tc = model->encoder == M6A_ENCODER_TC && model->d_tc_image != nullptr && bags == nullptr &&
                       sample_idx == nullptr && n_samples == 20;
   if (tile_reads <= 0 || (use_tc && model->tile_reads <= 0)) {
-    tile_reads = use_tc ? auto_tile_reads_tc(n_sites, total_reads) : auto_tile_reads(n_sites, total_reads, model->n_sms);
+    tile_reads = use_tc ? auto_tile_reads_tc(n_sites, total_reads, model->n_sms) : auto_tile_reads(n_sites, total_reads, model->n_sms);
   }
   a.tile_reads = tile_reads;
   a.site_stride = site_stride;

@@ -69,6 +69,9 @@ constexpr int kTmemCols = 512;
 constexpr uint32_t kColD1 = 0, kColALo = 2 * kN1, kColD2 = 2 * kN1 + 2 * kChunk;   // 0 | 320 | 384
 constexpr int kGroups = 2;                   // Linear-2 accumulator groups (chunks 0..2 | 3..4), each [main 32 | corr 32]
 constexpr int kGroup1Chunk = 3;              // first chunk of the second group
+#ifndef M6A_D2_SPLIT
+#define M6A_D2_SPLIT 0      // 1: D2 handed to E2 / back to the MMA issuer per accumulator group; 0: as a whole
+#endif
 static_assert(kColD2 + kGroups * 2 * kN2 == kTmemCols, "TMEM column budget");
 constexpr int kBarSe = 1, kBarE1 = 3;        // named barriers: staging / E2 groups (1, 2), E1 role (3)
 constexpr int kHalfCols = kChunk / 2;        // columns of a chunk per warp
@@ -101,6 +104,10 @@ struct alignas(128) TcSmem {
   float x[2][2][kK1 / 4][kTileM][4];            // 32 KB   A of Linear-1: [buffer][hi, lo][k-chunk][row][4]
   float fbuf[2][kK1][kTileM];                   // 16 KB   prefetched inputs of a group's next tile (cp.async), input-major:
                                                 //         [x(9) | emb | 1][row] -- lanes = rows, no bank conflicts
+#if M6A_D2_SPLIT
+  float g0[2][kN2][kTileM];                     // 32 KB   E2: (main + corr) of accumulator group 0, per E2 group, column-major
+                                                //         (thread = row: private, conflict-free) until group 1 is complete
+#endif
   float q[kSlots][kQCapT];                      // 72 KB   q = 1 - p of a slab (row order, or [group][entry][32 sites])
 #if M6A_TC_LANES_SITES
   float part[kSlots][2][kLaneBlocksMax][kOctets][32];   // 24 KB  lanes = sites pooling: b_k partial sums per (group, block)
@@ -119,10 +126,12 @@ struct alignas(128) TcSmem {
   alignas(8) unsigned long long l1_done[2];     // MMA commit    -> E1, staging : D1[b] ready / X[b] consumed
   alignas(8) unsigned long long a_full[2];      // E1 (256)      -> MMA : chunk staged in D1 (hi) / A_lo slot
   alignas(8) unsigned long long a_free[2];      // MMA commit    -> E1 : A_lo slot consumed
-  alignas(8) unsigned long long d2_full[2];     // MMA commit    -> E2 group (tile parity) : D2 complete.  One barrier per
-                                                // group: a parity wait must never be posted a phase early, and the groups
-                                                // take turns
-  alignas(8) unsigned long long d2_free[1];     // E2 (256)      -> MMA : D2 read out
+  // D2 is handed over per accumulator group: group 0 (chunks 0..2) is complete -- and is read out by E2 -- while the MMAs
+  // of chunks 3..4 still run, so Linear-2 of the next tile never waits for the read-out of a whole D2.
+  alignas(8) unsigned long long d2_full[kGroups][2];   // MMA commit -> E2 group (tile parity) : accumulator group complete.
+                                                // One barrier per E2 group: a parity wait must never be posted a phase
+                                                // early, and the groups take turns
+  alignas(8) unsigned long long d2_free[kGroups];      // E2 (128)   -> MMA : accumulator group read out
   int done[kSlots];                             // MC warps finished with the slab of a slot
   int maxn_scratch[2][4];
   alignas(8) unsigned long long slab_full[kSlots];   // E2 (128) -> MC
@@ -218,9 +227,11 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
         mbar_init(&sm.a_full[i], kRoleThreads);
         mbar_init(&sm.a_free[i], 1);
       }
-      mbar_init(&sm.d2_full[0], 1);
-      mbar_init(&sm.d2_full[1], 1);
-      mbar_init(&sm.d2_free[0], kTileM);
+      for (int i = 0; i < kGroups; ++i) {
+        mbar_init(&sm.d2_full[i][0], 1);
+        mbar_init(&sm.d2_full[i][1], 1);
+        mbar_init(&sm.d2_free[i], kTileM);
+      }
       for (int i = 0; i < kSlots; ++i) {
         mbar_init(&sm.slab_full[i], kTileM);
         mbar_init(&sm.slab_empty[i], 1);
@@ -239,7 +250,8 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
 
   if (warp == kMmaWarp) {
     // ======================================== MMA issuer ===================================================================
-    if (lane == 0) {
+    // The whole warp runs the loop (all state is warp-uniform) and one elected lane issues: see elect_one().
+    {
       constexpr uint32_t idesc1 = make_idesc(kTileM, kN1), idesc64 = make_idesc(kTileM, 2 * kN2), idesc32 = make_idesc(kTileM, kN2);
       // descriptors differ only in the start-address field (bits [0,14) = address >> 4): build once, add offsets
       const uint64_t dx0 = make_desc(smem_u32(sm.x[0][0]), kLboX, kSbo);
@@ -261,50 +273,58 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
           fence_after();
           const uint64_t ax = dx0 + b * kXBuf, axlo = ax + kXLo;
           const uint32_t d1 = tmem + kColD1 + b * kN1;
-          if (!(M6A_ABL & 4)) {
-          mma_ss(d1, ax, dw1hi, idesc1, 0u);
-          mma_ss_acc(d1, axlo, dw1hi, idesc1);
-          mma_ss_acc(d1, ax, dw1lo, idesc1);
-          mma_ss_acc(d1, ax + (kStepX >> 4), dw1hi + (kStepW1 >> 4), idesc1);
-          mma_ss_acc(d1, axlo + (kStepX >> 4), dw1hi + (kStepW1 >> 4), idesc1);
-          mma_ss_acc(d1, ax + (kStepX >> 4), dw1lo + (kStepW1 >> 4), idesc1);
+          if (elect_one()) {       // the commit is issued by the lane that issued the MMAs it tracks
+            if (!(M6A_ABL & 4)) {
+              mma_ss(d1, ax, dw1hi, idesc1, 0u);
+              mma_ss_acc(d1, axlo, dw1hi, idesc1);
+              mma_ss_acc(d1, ax, dw1lo, idesc1);
+              mma_ss_acc(d1, ax + (kStepX >> 4), dw1hi + (kStepW1 >> 4), idesc1);
+              mma_ss_acc(d1, axlo + (kStepX >> 4), dw1hi + (kStepW1 >> 4), idesc1);
+              mma_ss_acc(d1, ax + (kStepX >> 4), dw1lo + (kStepW1 >> 4), idesc1);
+            }
+            mma_commit(&sm.l1_done[b]);
           }
-          mma_commit(&sm.l1_done[b]);
         } else {
-          mbar_arrive(&sm.l1_done[b]);                            // wakes E1, which then reads the stop word
+          if (elect_one()) mbar_arrive(&sm.l1_done[b]);           // wakes E1, which then reads the stop word
         }
+        __syncwarp();
         PROF(1);
         // ---- Linear-2 of tile t-1, chunk by chunk as E1 stages them -----------------------------------------------------------
         if (t > 0) {
           const uint32_t u = t - 1, j = u & 1u;
           const uint32_t d1 = tmem + kColD1 + j * kN1;
-          mbar_wait(&sm.d2_free[0], (u & 1u) ^ 1u, kWaitD2Free);            // E2 has read D2 of tile u-1
+          mbar_wait(&sm.d2_free[0], (u & 1u) ^ 1u, kWaitD2Free);            // E2 has read group 0 of tile u-1
           PROF(2);
 #pragma unroll
           for (int c = 0; c < kChunks; ++c, ++g) {
             const uint32_t s = g & 1u;
+            if (M6A_D2_SPLIT && c == kGroup1Chunk) mbar_wait(&sm.d2_free[1], (u & 1u) ^ 1u, kWaitD2Free);   // ... and group 1
             mbar_wait(&sm.a_full[s], (g >> 1) & 1u, kWaitAFull);
             PROF(3);
             fence_after();
             const uint32_t a_lo = tmem + kColALo + s * kChunk;
             // two accumulator groups (K-steps of chunks 0..2 | 3..4): fewer truncating accumulations per accumulator
             const uint32_t d2 = tmem + kColD2 + (c >= kGroup1Chunk ? 2 * kN2 : 0);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < ((M6A_ABL & 4) ? 0 : kChunk / 8); ++ks) {
-              const int kstep = c * (kChunk / 8) + ks;
-              const uint64_t bw = dw2 + static_cast<uint64_t>(kstep) * (kStepW2 >> 4);
-              if (ks == 0 && (c == 0 || c == kGroup1Chunk)) mma_ts(d2, d1 + kstep * 8, bw, idesc64, 0u);   // [main | corr] = A_hi . [W2_hi ; W2_lo]^T
-              else mma_ts_acc(d2, d1 + kstep * 8, bw, idesc64);
-              mma_ts_acc(d2 + kN2, a_lo + ks * 8, bw, idesc32);            // corr += A_lo . W2_hi^T
+              for (int ks = 0; ks < ((M6A_ABL & 4) ? 0 : kChunk / 8); ++ks) {
+                const int kstep = c * (kChunk / 8) + ks;
+                const uint64_t bw = dw2 + static_cast<uint64_t>(kstep) * (kStepW2 >> 4);
+                if (ks == 0 && (c == 0 || c == kGroup1Chunk)) mma_ts(d2, d1 + kstep * 8, bw, idesc64, 0u);   // [main | corr] = A_hi . [W2_hi ; W2_lo]^T
+                else mma_ts_acc(d2, d1 + kstep * 8, bw, idesc64);
+                mma_ts_acc(d2 + kN2, a_lo + ks * 8, bw, idesc32);            // corr += A_lo . W2_hi^T
+              }
+              mma_commit(&sm.a_free[s]);
+              if (M6A_D2_SPLIT && c == kGroup1Chunk - 1) mma_commit(&sm.d2_full[0][j]);
+              if (c == kChunks - 1) mma_commit(&sm.d2_full[1][j]);
             }
-            mma_commit(&sm.a_free[s]);
+            __syncwarp();
             PROF(4);
           }
-          mma_commit(&sm.d2_full[j]);
         }
         if (stop) break;
       }
-      PROF_STORE(10, true);
+      PROF_STORE(10, lane == 0);
     }
   } else if (warp >= kE1Warp0 && warp < kE1Warp0 + kRoleWarps) {
     // ======================================== E1: relu + hi/lo split of D1, chunk by chunk ================================
@@ -570,7 +590,43 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
       // ---- (1) E2 of the tile staged one iteration ago: all 32 outputs of this row, 8 at a time ------------------------------
       if (ti_e.exists) {
         const uint32_t d2 = tmem + kColD2 + lane_base;
-        mbar_wait(&sm.d2_full[grp], (t_e >> 1) & 1u, kWaitD2Full);
+#if M6A_D2_SPLIT
+        // accumulator group 0 (chunks 0..2) is complete two chunks before the tile is: read it out and hand it back early
+        mbar_wait(&sm.d2_full[0][grp], (t_e >> 1) & 1u, kWaitD2Full);
+        fence_after();
+        PROF(7);
+        float* g0 = &sm.g0[grp][0][row];                           // (main + corr) of group 0: g0[k * kTileM]
+#pragma unroll
+        for (int o8 = 0; o8 < ((M6A_ABL & 8) ? 0 : kN2); o8 += 8) {
+          uint32_t m0[8], c0[8];
+          tmem_ld8(d2 + o8, m0);
+          tmem_ld8(d2 + kN2 + o8, c0);
+          wait_ld();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) g0[(o8 + k) * kTileM] = __uint_as_float(m0[k]) + __uint_as_float(c0[k]);
+        }
+        fence_before();
+        mbar_arrive(&sm.d2_free[0]);
+        mbar_wait(&sm.d2_full[1][grp], (t_e >> 1) & 1u, kWaitD2Full);
+        fence_after();
+        float z = sm.b3;
+#pragma unroll
+        for (int o8 = 0; o8 < ((M6A_ABL & 8) ? 0 : kN2); o8 += 8) {
+          uint32_t m1[8], c1[8];
+          tmem_ld8(d2 + 2 * kN2 + o8, m1);
+          tmem_ld8(d2 + 3 * kN2 + o8, c1);
+          wait_ld();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // (main + corr) of each accumulator group, groups added in K order, then the bias: all round-to-nearest float32
+            const float h2 = (g0[(o8 + k) * kTileM] + (__uint_as_float(m1[k]) + __uint_as_float(c1[k]))) + sm.b2[o8 + k];
+            z = fmaf(sm.w3[o8 + k], fmaxf(h2, 0.0f), z);
+          }
+        }
+        fence_before();
+        mbar_arrive(&sm.d2_free[1]);
+#else
+        mbar_wait(&sm.d2_full[1][grp], (t_e >> 1) & 1u, kWaitD2Full);
         fence_after();
         PROF(7);
         float z = sm.b3;
@@ -584,7 +640,6 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
           wait_ld();
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            // (main + corr) of each accumulator group, groups added in K order, then the bias: all round-to-nearest float32
             const float h2 = ((__uint_as_float(m0[k]) + __uint_as_float(c0[k])) + (__uint_as_float(m1[k]) + __uint_as_float(c1[k]))) +
                              sm.b2[o8 + k];
             z = fmaf(sm.w3[o8 + k], fmaxf(h2, 0.0f), z);
@@ -592,6 +647,7 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
         }
         fence_before();
         mbar_arrive(&sm.d2_free[0]);
+#endif
         PROF(8);
         const float p = 1.0f / (1.0f + expf(-z));
         if (ti_e.valid) {

@@ -96,9 +96,17 @@ struct Mwc64x {
   // two indices from one word (paired regime): the wide product's high half is the first index, its low half is a
   // fresh uniform word for the second
   M6A_HD void next_pair(uint32_t n, uint32_t& i1, uint32_t& i2) {
+#if defined(__CUDA_ARCH__)
+    // the halves of the wide product are taken apart in PTX: written as (t >> 32) << 2 the address of q[i1] becomes
+    // shift + mask + add (three instructions) instead of one LEA on the high register
+    uint32_t lo;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(i1) : "r"(next()), "r"(n));
+    i2 = mulhi_u32(lo, n);
+#else
     const uint64_t t = static_cast<uint64_t>(next()) * n;
     i1 = static_cast<uint32_t>(t >> 32);
     i2 = mulhi_u32(static_cast<uint32_t>(t), n);
+#endif
   }
 };
 

@@ -115,6 +115,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// One lane of a converged warp.  tcgen05.mma / tcgen05.commit take their operands from the uniform datapath: issued under this
+// predicate they compile to `ELECT; @P UTCHMMA`, whereas under `if (lane == 0)` ptxas wraps EVERY instruction in a
+// loop over the active lanes (ELECT / BRA.U.ANY, ~9 dependent instructions and a branch per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] . B[smem]^T
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
