@@ -581,6 +581,9 @@ mil_infer_tc_kernel(const KernelArgs a, const WeightImageTc* __restrict__ image)
         } else {
           // no tile left for this group: the group whose turn the next tile index is tells the MMA issuer to stop
           if (static_cast<int>(t_next & 1u) == grp) {
+            // x_full[grp] must not complete a second phase before the MMA issuer has consumed the first one (a parity wait
+            // that lags two phases never returns): the stop goes out only after Linear-1 of this group's last tile.
+            if (t_next >= 2) mbar_wait(&sm.l1_done[grp], ((t_next - 2) >> 1) & 1u, kWaitL1DoneSe);
             if (row == 0) sm.x_ctrl[t_next % kCtrlRing] = 0;
             mbar_arrive(&sm.x_full[grp]);
           }

@@ -69,9 +69,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 #if M6A_WAIT_SLEEP_NS > 0
     __nanosleep(M6A_WAIT_SLEEP_NS);
 #endif
-    if (trips >= (1u << 21)) {                       // ~1 s: every stuck wait leaves its record, the first one traps later
-      if (trips == (1u << 21)) mbar_wait_timeout(site, parity);
-      if (trips > (1u << 24)) __trap();
+    if (trips >= (1u << 16)) {                       // ~1 s (a trip is four try_waits of up to ~4 us): every stuck wait leaves its
+      if (trips == (1u << 16)) mbar_wait_timeout(site, parity);   // record, the first one traps a few seconds later
+      if (trips > (1u << 18)) __trap();
     }
   }
 }

@@ -192,6 +192,71 @@ def test_edge_cases_vs_oracle(n_reads_list, n_iters, n_samples):
     assert_mod_count(mc, orp, off, 0.05)
 
 
+@pytest.mark.parametrize("n_sites,n_reads", [(148, 50), (300, 50), (1000, 50), (5000, 50), (2000, 23), (777, 128), (40, 400)])
+def test_short_jobs_with_few_tiles_per_sm(n_sites, n_reads):
+    """Jobs of a few MMA tiles per SM: the tile size is balanced over the SMs, so a CTA gets one tile of 1-4 MMA tiles and its
+    two staging groups send the stop right after their last tile (the hand-over that once completed a barrier phase too
+    early).  Repeated, because the failure was a race; every site against the oracle once, bit-identical afterwards."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(n_sites * 131 + n_reads)
+    feats = rng.standard_normal((n_sites * n_reads, 9), dtype=np.float32)
+    off = np.arange(n_sites + 1, dtype=np.int64) * n_reads
+    kmer = rng.integers(0, 66, size=(n_sites, 3)).astype(np.int32)
+    eng = engine("HCT116_RNA002")
+    kw = dict(seed=2, site_id_base=5 * 10**9, read_threshold=0.033379376)
+    first = run_device(eng, feats, off, kmer, 1000, **kw)
+    orp, osp, omc = c_oracle.mil_inference(oracle_params("HCT116_RNA002"), feats, off, kmer, 1000, n_samples=20, **kw)
+    assert np.max(np.abs(first[0] - orp)) <= READ_ATOL
+    assert np.max(np.abs(first[1] - osp)) <= SITE_ATOL
+    assert_mod_count(first[2], orp, off, 0.033379376)
+    for _ in range(20):
+        again = run_device(eng, feats, off, kmer, 100, **kw)
+        assert np.array_equal(again[0], first[0])
+
+
+def test_random_job_shapes_both_encoders_agree(_both_encoders):
+    """Stress of the role hand-overs of the warp-specialised kernel: 120 random job shapes (site counts 1..4000, uniform,
+    ragged, with empty sites and with a site larger than the q table, random tile sizes) -- the two encoders are independent
+    implementations of the same expression, so they must agree to float32 round-off everywhere (and a lost arrival would trap)."""
+    if _both_encoders != "tc":
+        pytest.skip("one pass compares both encoders")
+    import torch
+    eng = engine("HCT116_RNA002")
+    rng = np.random.default_rng(2024)
+    for case in range(120):
+        kind = case % 4
+        n_sites = int(rng.integers(1, 4000))
+        if kind == 0:
+            n_reads = np.full(n_sites, int(rng.integers(1, 120)), dtype=np.int64)
+        elif kind == 1:
+            n_reads = np.clip(np.round(np.exp(rng.normal(np.log(30), 0.9, size=n_sites))), 1, 900).astype(np.int64)
+        elif kind == 2:
+            n_reads = rng.integers(0, 60, size=n_sites).astype(np.int64)
+            n_reads[rng.random(n_sites) < 0.3] = 0
+        else:
+            n_reads = rng.integers(20, 40, size=min(n_sites, 300)).astype(np.int64)
+            n_reads[int(rng.integers(0, len(n_reads)))] = int(rng.integers(6145, 9000))
+        feats, off, kmer = _random_case(rng, n_reads)
+        tile = 0 if case % 3 else int(rng.integers(1, 33)) * 128      # 0 = automatic
+        n_iters = int(rng.choice([1, 50, 300, 1000]))
+        out = {}
+        for enc in ("tc", "ffma"):
+            eng.set_encoder(enc)
+            f = torch.from_numpy(feats).to(eng.device)
+            o = torch.from_numpy(off).to(eng.device)
+            k = torch.from_numpy(kmer).to(eng.device)
+            eng.set_tile_reads(tile if enc == "tc" else 0)
+            rp, sp, mc = eng.infer_device(f, o, k, n_iters, seed=case, site_id_base=case * 10**6)
+            torch.cuda.synchronize()
+            eng.set_tile_reads(0)
+            out[enc] = (rp.cpu().numpy(), sp.cpu().numpy(), mc.cpu().numpy())
+        eng.set_encoder("tc")
+        live = n_reads > 0
+        assert np.max(np.abs(out["tc"][0] - out["ffma"][0]), initial=0) <= 3e-6, case
+        assert np.all(np.isnan(out["tc"][1][~live])) and np.all(out["tc"][2][~live] == 0), case
+        assert np.max(np.abs(out["tc"][1][live] - out["ffma"][1][live]), initial=0) <= SITE_ATOL, case
+
+
 def test_sharding_and_tiling_do_not_change_results(synthetic_inputs):
     """Counter-based RNG keyed by global site id + tiling-independent summation order: any split
     of the site list gives bit-identical outputs."""

@@ -105,6 +105,12 @@ for tag in ([] if "--no-parity" in sys.argv else (ALL_TAGS[:1] if "--first-only"
         o = np.concatenate([[0], np.cumsum(n)])
         f = rng.standard_normal((int(o[-1]), 9), dtype=np.float32)
         check("huge sites", eng, P, f, o, kmer[:6], 100, seed=9)
+        # short uniform jobs: the tile size is balanced over the SMs (tiles of 3-4 MMA tiles, one tile per CTA)
+        for S_ in (300, 1000, 5000):
+            f = rng.standard_normal((S_ * 50, 9), dtype=np.float32)
+            o = np.arange(S_ + 1, dtype=np.int64) * 50
+            k = rng.integers(0, 66, size=(S_, 3)).astype(np.int32)
+            check(f"{S_} x 50", eng, P, f, o, k, 1000, seed=2)
         # a uniform job large enough for every CTA: 40 000 sites x 50 reads, every site against the C oracle
         S, nr_ = 40_000, 50
         f = rng.standard_normal((S * nr_, 9), dtype=np.float32)
