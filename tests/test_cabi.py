@@ -97,6 +97,10 @@ def test_sass_shows_the_blackwell_native_paths():
     assert "UTCHMMA" not in ffma and "LDL" not in ffma                 # CUDA-core kernel: no tensor cores, no spills
     tc = sass.split("mil_infer_tc_kernelILi20")[1].split("Function :")[0]
     assert tc.count("UTCHMMA") >= 14 and "LDTM" in tc and "STTM" in tc and "UTCBAR" in tc and "LDGSTS" in tc
+    # the MMAs of a Linear-2 chunk are issued back to back by one elected lane of a converged warp (not one lane-loop per MMA)
+    ops = re.findall(r"/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", tc)
+    runs = max(len(m.group(0).split()) for m in re.finditer(r"(?:UTCHMMA )+", " ".join(ops) + " "))
+    assert runs >= 8 and "ELECT" in tc
     assert not re.search(r"\bHMMA\b", sass)                            # no legacy mma.sync anywhere
 
 

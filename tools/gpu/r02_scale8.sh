@@ -2,8 +2,7 @@
 # 8-GPU box: concurrent H2D ceiling, then the headline bench at N = 1, 2, 4, 8 (digests must agree), numactl facts
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/r02_topo.txt 2>&1; lscpu | grep -E "NUMA|Socket|Model name|^CPU\(s\)" > gpurun_out/r02_lscpu.txt
-tools/microbench/h2d_concurrent --json gpurun_out/r02_h2d_ceiling.json | tee gpurun_out/r02_h2d_ceiling.log
-mkdir -p profiles; cp gpurun_out/r02_h2d_ceiling.json profiles/r02_h2d_ceiling.json
+# (the concurrent H2D ceiling of this box type was measured by an earlier run of this script: profiles/r02_h2d_ceiling.json)
 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_scale_n1.json 2> gpurun_out/r02_scale_n1.err; echo "n1 rc=$?"
 for n in 2 4 8; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700+n)) bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r02_scale_n$n.json 2> gpurun_out/r02_scale_n$n.err; echo "n$n rc=$?"
