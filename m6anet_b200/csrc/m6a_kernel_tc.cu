@@ -6,20 +6,25 @@
 // tcgen05.mma chains per tile of 128 reads (error-compensated 3xTF32, m6a_layout.h), and the CUDA cores keep only the
 // relu / operand split, the sigmoid and the Monte-Carlo pooling.
 //
-// One persistent CTA per SM, 768 threads, warp-specialised; the roles run concurrently on DIFFERENT slabs
-// (slab = the <= 64 consecutive sites of one slice of a read-balanced tile, as in m6a_kernel.cu):
-//   warp 1        MMA issuer (one elected lane): Linear-1 of tile t+1 (6 MMAs M128 N160 K8, A and B from shared memory),
-//                 then per 32-column chunk of tile t: 8 MMAs (A from TMEM: N64 main|correction + N32 correction)
-//   warps 4..11   encoder epilogue, two per TMEM lane quadrant (each takes 16 of a chunk's 32 columns), thread = read:
-//                   X     gather [x(9) | emb(6) | 1] of tile t+1 -> RN_tf32 split -> shared memory (UMMA K-major layout)
-//                   E1    per chunk: tcgen05.ld D1 -> relu -> hi/lo split -> tcgen05.st hi IN PLACE (A operand of Linear-2)
-//                         and lo into a 2-slot staging ring -> mbarrier -> MMA issuer
-//                   E2    tile t-1: tcgen05.ld D2 (main + correction) -> +b2, relu, . w3, sigmoid -> read_prob (HBM),
-//                         q = 1 - p (shared memory of the slab slot), threshold count; last tile of a slab -> slab_full
-//   warps 0,2,3,12..23  Monte-Carlo pooling of a FINISHED slab (m6a_mc.cuh: warp per (site, block of 256 iterations),
-//                 Philox-seeded MWC64X lane streams), then site_prob / mod_count and slab_empty
-// TMEM (512 columns): D1[2] 2 x 160 | A_lo ring 2 x 32 | D2[2] 2 x (32 main + 32 correction).
-// Every mbarrier wait is bounded (a lost arrival traps instead of hanging the GPU).
+// One persistent CTA per SM, 1024 threads, warp-specialised; the roles run concurrently on DIFFERENT tiles / slabs
+// (slab = the <= 64 consecutive sites of one slice of a read-balanced tile, as in m6a_kernel.cu) and meet only at mbarriers:
+//   warp 31         MMA issuer.  The whole warp runs the loop, one elect.sync lane issues: Linear-1 of tile t (6 MMAs M128 N160
+//                   K8, A and B from shared memory), then per 32-column chunk of tile t-1: 8 MMAs (A from TMEM: N64
+//                   main|correction + N32 correction) and the tcgen05.commit that hands the chunk's A_lo slot back
+//   warps 20..27    E1, two per TMEM lane quadrant (each takes 16 of a chunk's 32 columns), thread = read: per chunk
+//                   tcgen05.ld D1 -> relu -> hi/lo split -> tcgen05.st hi IN PLACE (A operand of Linear-2) and lo into a
+//                   2-slot ring -> mbarrier -> MMA issuer
+//   warps 12..19    staging + E2, two groups of 4 warps taking the tiles alternately, thread = read:
+//                     X   cp.async prefetch of [x(9) | emb(6) | 1] -> RN_tf32 split -> shared memory (UMMA K-major layout)
+//                     E2  tcgen05.ld D2 (main + correction of two accumulator groups) -> +b2, relu, . w3, sigmoid ->
+//                         read_prob (HBM), q = 1 - p (shared memory of the slab slot), threshold count; last tile of a
+//                         slab -> slab_full
+//   warps 0..11, 28..30  Monte-Carlo pooling of a FINISHED slab (m6a_mc.cuh: a warp takes whole sites, the blocks of 256
+//                   iterations of a site are its interleaved chains; Philox-seeded MWC64X lane streams), then site_prob /
+//                   mod_count and slab_empty
+// TMEM (512 columns): D1[2] 2 x 160 | A_lo ring 2 x 32 | D2 = 2 accumulator groups x (32 main + 32 correction).
+// Every mbarrier wait is bounded (a lost arrival leaves a record in mapped host memory and traps instead of hanging the GPU).
+// Design notes, measurements and the experiments behind the constants below: DESIGN.md sections 4a and 7.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -49,15 +54,15 @@ constexpr int kSeWarp0 = 12;
 #endif
 constexpr int kRoleWarps = 8;
 constexpr int kRoleThreads = kRoleWarps * 32;   // 256
-constexpr int kMcWarps = 15;                 // warps 0, 2, 3, 20..31
+constexpr int kMcWarps = 15;                 // warps 0..11, 28..30 (layout 1)
 // 1: Monte-Carlo pooling with lanes = sites (site-interleaved q table, conflict-free loads) where the slab fits.  Measured on
-// B200 (1 M x 50 x 1000): 11.94 ms with it, 11.17 ms without -- the bank conflicts of the row-order table are not what
+// B200 (1 M x 50 x 1000): 11.15 ms with it, 10.51 ms without -- the bank conflicts of the row-order table are not what
 // limits the pooling; kept as an experiment (parity-checked, bit-identical site sums).
 #ifndef M6A_TC_LANES_SITES
 #define M6A_TC_LANES_SITES 0
 #endif
 #ifndef M6A_MC_CHAINS
-#define M6A_MC_CHAINS 2     // measured on B200 (1 M x 50 x 1000): 2 chains 12.84 ms, 4 chains 13.34 ms
+#define M6A_MC_CHAINS 2     // measured on B200 (1 M x 50 x 1000, final pipeline): 1 / 2 / 3 / 4 chains 10.66 / 10.47 / 11.73 / 11.48 ms
 #endif
 constexpr int kMcChains = M6A_MC_CHAINS;     // blocks of a site a Monte-Carlo warp interleaves
 #ifndef M6A_TC_SLOTS
