@@ -25,16 +25,21 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
+// v + (1 - prod) and the products themselves as separately rounded IEEE operations (never contracted into an FMA): every
+// pooling path -- one chain, two chains, packed products, the global-memory fallback -- evaluates the same float32
+// expression as the oracle, so a site's result does not depend on which path its slab takes.
+__device__ __forceinline__ float mc_accumulate(float v, float prod) { return __fadd_rn(v, __fsub_rn(1.0f, prod)); }
+
 // One draw step of a lane's chain in the paired (n <= 256, two indices per word) or single regime.
 template <bool PAIRED>
 __device__ __forceinline__ void mc_step(uint32_t qaddr, uint32_t n, Mwc64x& g, float& prod, bool second_of_pair_wanted = true) {
   if (PAIRED) {
     uint32_t i1, i2;
     g.next_pair(n, i1, i2);
-    prod *= lds_f32(qaddr + (i1 << 2));      // IMAD.WIDE, IMAD.HI, 2 x (LEA, LDS, FMUL) per word
-    if (second_of_pair_wanted) prod *= lds_f32(qaddr + (i2 << 2));
+    prod = __fmul_rn(prod, lds_f32(qaddr + (i1 << 2)));      // IMAD.WIDE, IMAD.HI, 2 x (LEA, LDS, FMUL) per word
+    if (second_of_pair_wanted) prod = __fmul_rn(prod, lds_f32(qaddr + (i2 << 2)));
   } else {
-    prod *= lds_f32(qaddr + (__umulhi(g.next(), n) << 2));   // IMAD.HI, LEA, LDS, FMUL
+    prod = __fmul_rn(prod, lds_f32(qaddr + (__umulhi(g.next(), n) << 2)));   // IMAD.HI, LEA, LDS, FMUL
   }
 }
 
@@ -47,7 +52,7 @@ __device__ __forceinline__ void mc_rounds(uint32_t qaddr, uint32_t n, Mwc64x& g,
 #pragma unroll
     for (int s = 0; s < kSteps; ++s) mc_step<PAIRED>(qaddr, n, g, prod);
     if (PAIRED && (NS & 1)) mc_step<PAIRED>(qaddr, n, g, prod, false);
-    v += 1.0f - prod;
+    v = mc_accumulate(v, prod);
   }
 }
 
@@ -68,8 +73,8 @@ __device__ __forceinline__ void mc_rounds_x2(uint32_t qa, uint32_t na, Mwc64x& g
       mc_step<PAIRED>(qa, na, ga, pa, false);
       mc_step<PAIRED>(qb, nb, gb, pb, false);
     }
-    va += 1.0f - pa;
-    vb += 1.0f - pb;
+    va = mc_accumulate(va, pa);
+    vb = mc_accumulate(vb, pb);
   }
 }
 
@@ -104,6 +109,9 @@ __device__ __forceinline__ void mc_lane_smem_x2(const float* qsa, uint32_t na, M
 // NC (site, block) items of the same index regime at once, chains interleaved instruction by instruction (the tensor-core
 // kernel has fewer Monte-Carlo warps than the CUDA-core kernel and hides the serial MWC latency inside each warp instead).
 // Identical results to NC mc_lane_smem calls: every chain accumulates its own rounds in round order.
+#ifndef M6A_MC_PACKED_MUL
+#define M6A_MC_PACKED_MUL 1
+#endif
 template <int NS, bool PAIRED, int NC>
 __device__ __forceinline__ void mc_rounds_xn(const uint32_t (&qa)[NC], const uint32_t (&n)[NC], Mwc64x (&g)[NC],
                                              const int (&rounds)[NC], float (&v)[NC]) {
@@ -111,21 +119,39 @@ __device__ __forceinline__ void mc_rounds_xn(const uint32_t (&qa)[NC], const uin
   int kc = rounds[0];
 #pragma unroll
   for (int i = 1; i < NC; ++i) kc = min(kc, rounds[i]);
-  for (int k = 0; k < kc; ++k) {
-    float p[NC];
+  if constexpr (M6A_MC_PACKED_MUL && NC == 2 && PAIRED && (NS & 1) == 0) {
+    // the products of the two chains as one packed multiply (FMUL2: two IEEE multiplies, one issue slot)
+    for (int k = 0; k < kc; ++k) {
+      float2 p;
 #pragma unroll
-    for (int i = 0; i < NC; ++i) p[i] = 1.0f;
-#pragma unroll
-    for (int s = 0; s < kSteps; ++s) {
-#pragma unroll
-      for (int i = 0; i < NC; ++i) mc_step<PAIRED>(qa[i], n[i], g[i], p[i]);
+      for (int s = 0; s < kSteps; ++s) {
+        uint32_t a1, a2, b1, b2;
+        g[0].next_pair(n[0], a1, a2);
+        g[1].next_pair(n[1], b1, b2);
+        const float2 q1 = make_float2(lds_f32(qa[0] + (a1 << 2)), lds_f32(qa[1] + (b1 << 2)));
+        p = s == 0 ? q1 : __fmul2_rn(p, q1);                       // (1.0f * q is q: the first factor starts the product)
+        p = __fmul2_rn(p, make_float2(lds_f32(qa[0] + (a2 << 2)), lds_f32(qa[1] + (b2 << 2))));
+      }
+      v[0] = mc_accumulate(v[0], p.x);
+      v[1] = mc_accumulate(v[1], p.y);
     }
-    if (PAIRED && (NS & 1)) {
+  } else {
+    for (int k = 0; k < kc; ++k) {
+      float p[NC];
 #pragma unroll
-      for (int i = 0; i < NC; ++i) mc_step<PAIRED>(qa[i], n[i], g[i], p[i], false);
+      for (int i = 0; i < NC; ++i) p[i] = 1.0f;
+#pragma unroll
+      for (int s = 0; s < kSteps; ++s) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) mc_step<PAIRED>(qa[i], n[i], g[i], p[i]);
+      }
+      if (PAIRED && (NS & 1)) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) mc_step<PAIRED>(qa[i], n[i], g[i], p[i], false);
+      }
+#pragma unroll
+      for (int i = 0; i < NC; ++i) v[i] = mc_accumulate(v[i], p[i]);
     }
-#pragma unroll
-    for (int i = 0; i < NC; ++i) v[i] += 1.0f - p[i];
   }
 #pragma unroll
   for (int i = 0; i < NC; ++i) mc_rounds<NS, PAIRED>(qa[i], n[i], g[i], kc, rounds[i], v[i]);   // ragged tails
@@ -151,9 +177,9 @@ __device__ __forceinline__ float mc_lane_generic(const float* qbase, bool from_p
       } else {
         i = pending;
       }
-      prod *= from_prob ? 1.0f - qbase[i] : qbase[i];
+      prod = __fmul_rn(prod, from_prob ? __fsub_rn(1.0f, qbase[i]) : qbase[i]);
     }
-    v += 1.0f - prod;
+    v = mc_accumulate(v, prod);
   }
   return v;
 }
