@@ -1,3 +1,4 @@
+// FMUL2 (packed f32x2 multiply) semantics check on the GPU: elementwise, halves fed by separate loads.  nvcc -O3 -gencode arch=compute_100a,code=sm_100a
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void k(const float2* a, const float2* b, float2* o, float* o2) {
