@@ -128,6 +128,9 @@ const char *m6a_build_info(void);
 int m6a_model_set_tile_reads(m6a_model_t *model, int32_t tile_reads);
 /* The automatic choice for a job of n_sites sites / total_reads rows on a device with n_sms SMs (introspection). */
 int32_t m6a_auto_tile_reads(int64_t n_sites, int64_t total_reads, int32_t n_sms);
+/* The same for the tensor-core encoder: 64 sites' worth of rows (<= 6144), shrunk to total / (rounds x SMs) rounded up to whole
+ * 128-row MMA tiles when the job is fewer than 64 rounds of tiles long, so that the last round is as full as the others. */
+int32_t m6a_auto_tile_reads_tc(int64_t n_sites, int64_t total_reads, int32_t n_sms);
 
 /*
  * Score n_sites sites.  All data pointers are DEVICE pointers.

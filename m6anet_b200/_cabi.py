@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("M6A_LIB") or os.path.join(_HERE, "libm6anet_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 EXPORTS = (
-    "m6a_version", "m6a_strerror", "m6a_device_count", "m6a_set_device", "m6a_model_create", "m6a_model_destroy", "m6a_model_set_tile_reads", "m6a_auto_tile_reads", "m6a_mil_workspace_bytes",
+    "m6a_version", "m6a_strerror", "m6a_device_count", "m6a_set_device", "m6a_model_create", "m6a_model_destroy", "m6a_model_set_tile_reads", "m6a_auto_tile_reads", "m6a_auto_tile_reads_tc", "m6a_mil_workspace_bytes",
     "m6a_mil_infer_f32", "m6a_mil_infer_packed_f32", "m6a_model_set_encoder", "m6a_model_get_encoder", "m6a_debug_trap_record",
     "m6a_pinned_alloc", "m6a_pinned_free", "m6a_build_info",
     "m6a_mil_infer_host_f32", "m6a_sample_indices", "m6a_mil_validate_f32", "m6a_mil_validate_host_f32", "m6a_sample_bags",
@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
     L.m6a_build_info.argtypes = []
     L.m6a_auto_tile_reads.restype = i32
     L.m6a_auto_tile_reads.argtypes = [i64, i64, i32]
+    L.m6a_auto_tile_reads_tc.restype = i32
+    L.m6a_auto_tile_reads_tc.argtypes = [i64, i64, i32]
     L.m6a_mil_workspace_bytes.restype = i64
     L.m6a_mil_workspace_bytes.argtypes = [i64]
     L.m6a_mil_infer_host_f32.restype = C.c_int

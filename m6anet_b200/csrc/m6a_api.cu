@@ -416,6 +416,10 @@ extern "C" int32_t m6a_auto_tile_reads(int64_t n_sites, int64_t total_reads, int
   return auto_tile_reads(n_sites, total_reads, n_sms > 0 ? n_sms : 148);
 }
 
+extern "C" int32_t m6a_auto_tile_reads_tc(int64_t n_sites, int64_t total_reads, int32_t n_sms) {
+  return auto_tile_reads_tc(n_sites, total_reads, n_sms > 0 ? n_sms : 148);
+}
+
 extern "C" int64_t m6a_mil_workspace_bytes(int64_t total_reads) {
   if (total_reads < 0) return 0;
   return (total_reads / 64 + 3) * static_cast<int64_t>(sizeof(long long));   // tiles hold >= 64 rows: n_tiles + 1 bounds + 1 counter

@@ -115,3 +115,19 @@ def test_auto_tile_reads_policy(lib):
     assert t(1_000_000, 47_900_123) == 1000            # uneven sites
     assert t(10, 7) == 500 and t(0, 0) >= 64
     assert lib.m6a_mil_workspace_bytes(50_000_000) >= (50_000_000 // 500 + 2) * 8
+
+
+def test_auto_tile_reads_policy_tensor_core_kernel(lib):
+    """Rows per tile of the tensor-core kernel: 64 sites' worth (no padded MMA rows for even depths), and for jobs of fewer
+    than 64 rounds of tiles a tile shrunk so that every SM gets the same number of whole tiles (multiples of 128 rows)."""
+    t = lambda s, r: lib.m6a_auto_tile_reads_tc(s, r, 148)
+    assert t(1_000_000, 50_000_000) == 3200            # headline job: 64 sites of 50 reads, 105.6 -> 106 rounds: unchanged
+    assert t(1_000_000, 20_000_000) == 1280            # config 2 shape: 64 sites of 20 reads
+    assert t(125_000, 6_250_000) == 3072               # one N=8 shard: 13.2 rounds of 3200 -> 14 rounds of 3072
+    assert t(1000, 50_000) == 384                      # one tile of 3 MMA tiles per SM (the shape that once lost a hand-over)
+    assert t(288, 14_108) == 2048                      # ragged and tiny: below 256 rows per SM the default stays
+    assert t(1_000_000, 47_900_123) == 2048            # uneven sites, long job
+    for s, r in [(1, 20), (10, 7), (0, 0), (5_000, 250_000), (40, 16_000), (3, 30_000)]:
+        v = t(s, r)
+        assert 64 <= v <= 6144
+        assert lib.m6a_mil_workspace_bytes(r) >= (r // v + 3) * 8          # bounds + counter fit the documented workspace
