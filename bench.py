@@ -77,6 +77,11 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-digest", action="store_true")
+    ap.add_argument("--cli", action="store_true",
+                    help="also run the drop-in CLI leg (SURVEY.md 8f rows 1-2): a synthetic data.json of --cli-sites x --reads "
+                         "through `python -m m6anet_b200 inference` into both CSVs; wall time and per-stage rates under the "
+                         "key `cli` (rank 0, N=1 only; tools/gpu_cli_timing.py)")
+    ap.add_argument("--cli-sites", type=int, default=100_000)
     ap.add_argument("--tile-reads", type=int, default=0, help="override the kernel's feature rows per tile (0 = automatic)")
     ap.add_argument("--ragged", action="store_true", help="robustness run: lognormal n_reads (median 33, clip [20, 1000]) "
                     "instead of the constant --reads of the headline job (SURVEY.md section 8d)")
@@ -563,6 +568,17 @@ def main():
                "sample": f"first {n_sample} sites of the job ({int(off_h[n_sample])} reads): {how}; encoder "
                          f"{r['t_encoder_s']:.3f}s + MC {r['t_mc_s']:.3f}s"}
 
+    # ---- optional CLI leg: data.json -> CSVs through the drop-in command (rank 0, N=1 only) ----------------------------
+    cli = None
+    if rank == 0 and world == 1 and a.cli:
+        import subprocess
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_cli_timing.py"), str(a.cli_sites), str(a.reads)],
+                           capture_output=True, text=True, cwd=ROOT)
+        try:
+            cli = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception:                                            # noqa: BLE001
+            cli = {"error": (r.stderr or r.stdout)[-400:]}
+
     rc = 0
     if rank == 0:
         line = {
@@ -575,6 +591,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "result_digest": digest,
             "clocks": clocks, "gpu_launches": a.steps * launch["n_launches"],
         }
+        if cli is not None:
+            line["cli"] = cli
         print(json.dumps(line), flush=True)
         if parity is not None and not parity["ok"]:
             print(f"bench.py: PARITY FAILED {parity}", file=sys.stderr)
