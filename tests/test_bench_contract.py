@@ -74,3 +74,23 @@ def test_b200_arm_line():
     assert e["matches_resident_path"] is True
     assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_synthetic_job_does_not_depend_on_the_sharding(ragged):
+    """The job bench.py scores is generated in fixed blocks of sites: the shards of a 1-, 2-, 3-, 4- or 8-rank run put together
+    are the same arrays bit for bit -- which is what makes the `result_digest` of the SCALE lines comparable."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    total, n_reads = 4003, 23
+    whole = bench.synth_shard(0, total, n_reads, 7, ragged=ragged, total_sites=total)
+    assert whole[1][0] == 0 and whole[1][-1] == len(whole[0]) and whole[2].shape == (total, 3)
+    for world in (2, 3, 4, 8):
+        cuts = [total * r // world for r in range(world + 1)]
+        parts = [bench.synth_shard(cuts[r], cuts[r + 1], n_reads, 7, ragged=ragged, total_sites=total) for r in range(world)]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), whole[0])
+        assert np.array_equal(np.concatenate([p[2] for p in parts]), whole[2])
+        assert np.array_equal(np.concatenate([np.diff(p[1]) for p in parts]), np.diff(whole[1]))
